@@ -1,0 +1,668 @@
+// fe_step.cu — the vectorised trading-env step of hmomin/FinEnvs as hand-written sm_100a CUDA.
+//
+// One launch per step does what finenvs/environments/time_series_env.py:277-536 does in ~660
+// torch-eager ops: advance the time pointer, read the current OHLC bar, map the action to trades
+// with cash / position / margin / commission bookkeeping, build the observation window, compute
+// the reward, detect episode end, auto-reset (with counter-based redraws) and keep the
+// evaluate-mode metrics.  The arithmetic follows the reference op for op, dtype for dtype
+// (SURVEY.md App. A): f32 state, f64 temporaries rounded once, no FMA contraction (every
+// product/sum below is an explicit __*_rn intrinsic, and the TU is built with -fmad=false).
+//
+// Data movement (the part that costs time: ~2.2 KB per env-step at W=60, <100 flops):
+//   tile variant   — each env's W x 16 B log-return window is fetched with one 1-D bulk async
+//                    copy (cp.async.bulk, SASS UBLKCP) into shared memory, completing on an
+//                    mbarrier; the block interleaves the position feature (4 -> 5 values per row,
+//                    conflict-free stride-5 STS) into an output tile that is contiguous in the
+//                    (N, W, 5) observation tensor and leaves with one bulk async store.
+//   direct variant — warp-per-env global->global copy for windows that do not fit in smem.
+//
+// The C ABI is declared in include/finenvs_b200.h.
+#include "finenvs_b200.h"
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace {
+
+constexpr int kThreads = 128;          // threads per block (both variants)
+constexpr int kMaxTileEnvs = kThreads; // one bookkeeping thread per env of the tile
+constexpr int kSmemHeader = 16;        // mbarrier (8 B) + pad
+constexpr int kSmemTarget = 72 * 1024; // aim for 3 resident blocks per SM
+constexpr int kSmemMax = 226 * 1024;
+
+// ------------------------------------------------------------------------------------------
+// exact (never contracted) arithmetic helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float d2f(double a) { return __double2float_rn(a); }
+// torch.relu keeps NaN (clamp_min), unlike fmax
+__device__ __forceinline__ float relu32(float x) { return x < 0.0f ? 0.0f : x; }
+__device__ __forceinline__ double relu64(double x) { return x < 0.0 ? 0.0 : x; }
+
+struct Consts {
+    float ms, scale, cf, imrf, SBf;
+    double c, imr, mmr1, SB;
+};
+
+Consts make_consts(const FeParams &p) {
+    Consts k;
+    k.ms = (float)p.max_shares;
+    k.scale = (float)((double)p.max_shares + 0.5); // :299  f32 tensor * python float
+    k.cf = (float)p.commission;                    // :364
+    k.imrf = (float)p.imr;                         // :377-378
+    k.SBf = (float)p.starting_balance;             // :499
+    k.c = p.commission;
+    k.imr = p.imr;
+    k.mmr1 = 1.0 + p.mmr;                          // :462
+    k.SB = p.starting_balance;
+    return k;
+}
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 keyed (seed) with counter (env id, step | kind<<63): the redraw RNG
+// (replaces torch.randint at :253 / :511; identical on host, see fe_philox)
+// ------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ void philox4x32_10(uint64_t seed, uint64_t env_id, uint64_t step,
+                                                       uint32_t kind, uint32_t out[4]) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    uint32_t c0 = (uint32_t)env_id, c1 = (uint32_t)(env_id >> 32), c2 = (uint32_t)step,
+             c3 = ((uint32_t)(step >> 32) & 0x7FFFFFFFu) | (kind << 31);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ void draw_segment(const FeParams &p, const FeSeries &s, int64_t gid, uint64_t step,
+                                             uint32_t kind, int32_t &seg, int32_t &off) {
+    uint32_t r[4];
+    philox4x32_10(p.seed, (uint64_t)gid, step, kind, r);
+    seg = (int32_t)__umulhi(r[0], (uint32_t)p.num_segments);
+    off = 0;
+    if (p.random_offset) {
+        // valid start pointers are 0 .. seg_len - W - 1 (one bar must remain to step onto)
+        const int32_t span = __ldg(s.seg_len + seg) - p.window;
+        off = span > 0 ? (int32_t)__umulhi(r[1], (uint32_t)span) : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// per-env bookkeeping: everything of step() except moving the window
+// ------------------------------------------------------------------------------------------
+struct EnvResult {
+    int64_t row0;   // first row of the observation window in the flat series
+    double posfeat; // (long - short) * close / starting_balance  (:428-431)
+    int done;
+    int newly_terminated;
+    double fin_return; // episode return of an env that finished this step (stats)
+    int fin_len;
+};
+
+// reset() (:423-435): no state change, current window + position feature
+__device__ __forceinline__ EnvResult env_observe(const FeParams &p, const FeSeries &s, const FeState &st,
+                                                 const Consts &k, int64_t i) {
+    EnvResult r;
+    r.row0 = __ldg(s.seg_start + st.seg[i]) + st.ptr[i];
+    const double C = __ldg(s.prices + (r.row0 + p.window - 1) * 4 + 3);
+    const float net = fsub(st.long_sh[i], st.short_sh[i]);
+    r.posfeat = __ddiv_rn(dmul((double)net, C), k.SB);
+    r.done = 0; r.newly_terminated = 0; r.fin_return = 0.0; r.fin_len = 0;
+    return r;
+}
+
+template <typename OutT>
+__device__ __forceinline__ EnvResult env_step(const FeParams &p, const FeSeries &s, const FeState &st,
+                                              const Consts &k, int64_t i, const float *__restrict__ actions,
+                                              OutT *__restrict__ rewards, int32_t *__restrict__ dones,
+                                              bool track, uint64_t step) {
+    EnvResult res;
+    const int W = p.window;
+    // :298-302 action -> integer share delta (round half to even, then clamp)
+    float d = rintf(fmul(__ldg(actions + i), k.scale));
+    d = d < -k.ms ? -k.ms : (d > k.ms ? k.ms : d);
+    // :281-282 advance time
+    int32_t seg = st.seg[i];
+    int32_t ptr = st.ptr[i] + 1;
+    const int32_t len = __ldg(s.seg_len + seg);
+    res.row0 = __ldg(s.seg_start + seg) + ptr;
+    // :323-342 current bar = last row of the window: O,H,L,C as two 16-byte loads
+    const double2 *px = reinterpret_cast<const double2 *>(s.prices + (res.row0 + W - 1) * 4);
+    const double2 oh = __ldg(px), lc = __ldg(px + 1);
+    const double O = oh.x, H = oh.y, L = lc.x, C = lc.y;
+    float cash = st.cash[i];
+    float lng = st.long_sh[i];
+    float sht = st.short_sh[i];
+    double margin = st.margin[i];
+    float comm = 0.0f; // :305
+    // :344-351
+    float pos = d < 0.0f ? 0.0f : d;
+    float neg = d > 0.0f ? 0.0f : d;
+    const double Omc = dsub(O, k.c), Opc = dadd(O, k.c);
+    { // :353-361 sell longs (+ :363-365)
+        const float nl = relu32(fadd(lng, neg));
+        const float sold = fsub(lng, nl);
+        neg = fadd(neg, sold);
+        comm = fadd(comm, fmul(sold, k.cf));
+        cash = d2f(dadd((double)cash, dmul((double)sold, Omc)));
+        lng = nl;
+    }
+    { // :367-383 cover shorts, re-mark margin to imr * short * open
+        const float ns = relu32(fsub(sht, pos));
+        const float bought = fsub(sht, ns);
+        pos = fsub(pos, bought);
+        comm = fadd(comm, fmul(bought, k.cf));
+        cash = d2f(dsub((double)cash, dmul((double)bought, Opc)));
+        sht = ns;
+        const double nm = dmul((double)fmul(k.imrf, sht), O);
+        cash = d2f(dsub((double)cash, dsub(nm, margin)));
+        margin = nm;
+    }
+    // :385-392 all-or-nothing long entry
+    if (dsub((double)cash, dmul((double)pos, Opc)) < 0.0) pos = 0.0f;
+    // :394-399
+    comm = fadd(comm, fmul(pos, k.cf));
+    cash = d2f(dsub((double)cash, dmul((double)pos, Opc)));
+    lng = fadd(lng, pos);
+    { // :401-410 all-or-nothing short entry, :412-421 open short
+        float q = -neg;
+        float sc = fmul(q, k.cf);
+        double req = dmul(k.imr, dmul((double)q, O));
+        if (dsub(dsub((double)cash, req), (double)sc) < 0.0) {
+            q = -0.0f; // neg = 0 -> -neg
+            sc = fmul(q, k.cf);
+            req = dmul(k.imr, dmul((double)q, O));
+        }
+        comm = fadd(comm, fmul(q, k.cf));
+        cash = d2f(dsub((double)cash, dadd(req, (double)sc)));
+        margin = dadd(margin, req);
+        sht = fadd(sht, q);
+    }
+    // :321 -> reset(): the observation is built NOW, before rewards / dones / auto-reset
+    res.posfeat = __ddiv_rn(dmul((double)fsub(lng, sht), C), k.SB);
+    // :447-457 rewards
+    int done = cash < 0.0f; // :448
+    double rew;
+    {
+        // :459-468 maintenance margin at High
+        const double mc1 = relu64(dsub(dmul(dmul((double)sht, H), k.mmr1), margin));
+        cash = d2f(dsub((double)cash, mc1));
+        margin = dadd(margin, mc1);
+        done |= cash < 0.0f;
+        // :470-475 margin release at Low
+        const double rel = relu64(dsub(margin, dmul(dmul((double)sht, L), k.imr)));
+        margin = dsub(margin, rel);
+        cash = d2f(dadd((double)cash, rel));
+        // :451 maintenance margin at Close
+        const double mc2 = relu64(dsub(dmul(dmul((double)sht, C), k.mmr1), margin));
+        cash = d2f(dsub((double)cash, mc2));
+        margin = dadd(margin, mc2);
+        done |= cash < 0.0f;
+        rew = dadd(-mc1, -mc2);
+        if (done) { lng = 0.0f; sht = 0.0f; } // :452-453
+        rew = dadd(rew, dmul((double)fsub(lng, sht), dsub(C, O))); // :454-455
+        rew = dsub(rew, (double)comm);                              // :456
+    }
+    // :477-496 time limit / NaN padding == pointer ran into the end of the (effective) segment
+    done |= (ptr + W >= len);
+    // :288-289 closing commission on whatever is still held
+    rew = dsub(rew, (double)fmul(fmul(done ? 1.0f : 0.0f, fadd(sht, lng)), k.cf));
+    // :498-521 auto-reset
+    if (done) {
+        cash = k.SBf; margin = 0.0; lng = 0.0f; sht = 0.0f; ptr = 0;
+        const int64_t gid = p.env_id_base + i;
+        if (p.reset_mode == FE_RESET_ALL || (p.reset_mode == FE_RESET_LAST && gid == p.total_envs - 1)) {
+            draw_segment(p, s, gid, step, 0u, seg, ptr);
+            st.seg[i] = seg;
+        }
+    }
+    res.done = done;
+    res.newly_terminated = 0; res.fin_return = 0.0; res.fin_len = 0;
+    if (p.evaluate) { // :523-536
+        const int was = st.terminated[i];
+        if (was) rew = 0.0;                                             // :527-528
+        if (done && !was) { st.terminated[i] = 1; res.newly_terminated = 1; } // :529
+        st.ep_return[i] = d2f(dadd((double)st.ep_return[i], rew));      // :530  f32 += f64
+    } else if (track) { // extension: running episode return / length for the NCCL-reduced statistics
+        const float er = d2f(dadd((double)st.ep_return[i], rew));
+        const int32_t el = st.ep_len[i] + 1;
+        if (done) { res.fin_return = (double)er; res.fin_len = el; }
+        st.ep_return[i] = done ? 0.0f : er;
+        st.ep_len[i] = done ? 0 : el;
+    }
+    st.ptr[i] = ptr; st.cash[i] = cash; st.long_sh[i] = lng; st.short_sh[i] = sht; st.margin[i] = margin;
+    rewards[i] = (OutT)rew;
+    dones[i] = done; // :296 dones.int()
+    return res;
+}
+
+// one atomic per warp for the episode statistics
+__device__ __forceinline__ void accumulate_stats(FeStats *stats, const EnvResult &r, bool active) {
+    if (stats == nullptr) return;
+    const unsigned full = 0xFFFFFFFFu;
+    const int done = active ? r.done : 0;
+    const int nterm = active ? r.newly_terminated : 0;
+    const unsigned nd = __reduce_add_sync(full, (unsigned)done);
+    const unsigned nt = __reduce_add_sync(full, (unsigned)nterm);
+    if (nd == 0 && nt == 0) return;
+    unsigned sl = __reduce_add_sync(full, (unsigned)(done ? r.fin_len : 0));
+    double sr = done ? r.fin_return : 0.0;
+    double sq = sr * sr;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sr += __shfl_xor_sync(full, sr, o);
+        sq += __shfl_xor_sync(full, sq, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (nd) atomicAdd(&stats->n_done, (unsigned long long)nd);
+        if (nt) atomicAdd(&stats->n_terminated, (unsigned long long)nt);
+        if (sl) atomicAdd(&stats->sum_len, (unsigned long long)sl);
+        if (nd) { atomicAdd(&stats->sum_return, sr); atomicAdd(&stats->sum_return_sq, sq); }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers: mbarrier + 1-D bulk async copies (TMA engine, no tensor map needed)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// global -> shared, completes `bytes` on the mbarrier
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// shared -> global
+__device__ __forceinline__ void bulk_store(void *dst, uint32_t src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------
+// tile variant
+// ------------------------------------------------------------------------------------------
+template <typename OutT> struct Row4;
+template <> struct Row4<float> { float4 v; };
+template <> struct Row4<double> { double2 a, b; };
+
+// smem layout: [mbarrier 16 B][posfeat E x OutT, padded to 16 B][in tile E*W*4 OutT][out tile E*W*5 OutT]
+template <typename OutT> __host__ __device__ constexpr size_t tile_pf_bytes(int E) {
+    return ((size_t)E * sizeof(OutT) + 15) & ~(size_t)15;
+}
+template <typename OutT> __host__ __device__ inline size_t tile_smem_bytes(int E, int W) {
+    return kSmemHeader + tile_pf_bytes<OutT>(E) + (size_t)E * W * 9 * sizeof(OutT);
+}
+
+template <typename OutT, bool kObserve>
+__global__ void __launch_bounds__(kThreads)
+fe_tile_kernel(const FeParams p, const FeSeries s, const FeState st, const Consts k, const float *__restrict__ actions,
+               OutT *__restrict__ obs, OutT *__restrict__ rewards, int32_t *__restrict__ dones, FeStats *stats,
+               const uint64_t step, const int E) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int W = p.window;
+    const int tid = threadIdx.x;
+    const int64_t env0 = (int64_t)blockIdx.x * E;
+    const int nvalid = (int)min((int64_t)E, p.num_envs - env0);
+    OutT *pf = reinterpret_cast<OutT *>(smem + kSmemHeader);
+    unsigned char *in_tile = smem + kSmemHeader + tile_pf_bytes<OutT>(E);
+    OutT *out_tile = reinterpret_cast<OutT *>(in_tile + (size_t)E * W * 4 * sizeof(OutT));
+    const uint32_t bar = smem_u32(smem);
+    const uint32_t row_bytes = 4 * sizeof(OutT);
+    const uint32_t win_bytes = (uint32_t)W * row_bytes;
+
+    if (tid == 0) {
+        mbar_init(bar, (uint32_t)nvalid);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // ---- one thread per env: fetch its window asynchronously, do the bookkeeping meanwhile ----
+    const bool active = tid < nvalid;
+    EnvResult r;
+    r.done = 0; r.newly_terminated = 0; r.fin_return = 0.0; r.fin_len = 0;
+    if (active) {
+        const int64_t i = env0 + tid;
+        // window start is known before any arithmetic: launch the copy first
+        const int64_t row0 = __ldg(s.seg_start + st.seg[i]) + st.ptr[i] + (kObserve ? 0 : 1);
+        mbar_arrive_expect_tx(bar, win_bytes);
+        bulk_load(smem_u32(in_tile + (size_t)tid * win_bytes),
+                  reinterpret_cast<const unsigned char *>(s.logret) + (size_t)row0 * row_bytes, win_bytes, bar);
+        if (kObserve) r = env_observe(p, s, st, k, i);
+        else r = env_step<OutT>(p, s, st, k, i, actions, rewards, dones, stats != nullptr, step);
+        pf[tid] = (OutT)r.posfeat;
+    }
+    if (!kObserve && tid < ((nvalid + 31) & ~31)) accumulate_stats(stats, r, active);
+    __syncthreads(); // pf visible
+    mbar_wait(bar, 0); // all windows landed
+
+    // ---- interleave: row (4 values) + position feature -> 5 values, rows are contiguous in both tiles
+    const int nrows = nvalid * W;
+    const float invW = 1.0f / (float)W;
+    const Row4<OutT> *in_rows = reinterpret_cast<const Row4<OutT> *>(in_tile);
+    for (int row = tid; row < nrows; row += kThreads) {
+        const int e = __float2int_rz(((float)row + 0.5f) * invW);
+        const Row4<OutT> v = in_rows[row];
+        OutT *o = out_tile + (size_t)row * 5;
+        if constexpr (sizeof(OutT) == 4) {
+            o[0] = v.v.x; o[1] = v.v.y; o[2] = v.v.z; o[3] = v.v.w;
+        } else {
+            o[0] = v.a.x; o[1] = v.a.y; o[2] = v.b.x; o[3] = v.b.y;
+        }
+        o[4] = pf[e];
+    }
+    // ---- out tile -> obs[env0 : env0+nvalid] (contiguous): one bulk async store
+    const size_t out_bytes = (size_t)nrows * 5 * sizeof(OutT);
+    OutT *dst = obs + (size_t)env0 * W * 5;
+    if ((out_bytes & 15) == 0) {
+        fence_proxy_async_smem(); // generic-proxy smem writes -> visible to the async proxy
+        __syncthreads();
+        if (tid == 0) {
+            bulk_store(dst, smem_u32(out_tile), (uint32_t)out_bytes);
+            bulk_commit();
+            bulk_wait_read_all(); // smem must outlive the read side of the store
+        }
+    } else { // ragged tail block whose byte count is not a multiple of 16
+        __syncthreads();
+        for (int f = tid; f < nrows * 5; f += kThreads) dst[f] = out_tile[f];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// direct variant: any window; thread-per-env bookkeeping, then warp-per-env copy
+// ------------------------------------------------------------------------------------------
+template <typename OutT, bool kObserve>
+__global__ void __launch_bounds__(kThreads)
+fe_direct_kernel(const FeParams p, const FeSeries s, const FeState st, const Consts k, const float *__restrict__ actions,
+                 OutT *__restrict__ obs, OutT *__restrict__ rewards, int32_t *__restrict__ dones, FeStats *stats,
+                 const uint64_t step) {
+    __shared__ int64_t sh_row0[kThreads];
+    __shared__ OutT sh_pf[kThreads];
+    const int W = p.window;
+    const int tid = threadIdx.x;
+    const int64_t env0 = (int64_t)blockIdx.x * kThreads;
+    const int nvalid = (int)min((int64_t)kThreads, p.num_envs - env0);
+    const bool active = tid < nvalid;
+    EnvResult r;
+    r.done = 0; r.newly_terminated = 0; r.fin_return = 0.0; r.fin_len = 0; r.row0 = 0; r.posfeat = 0.0;
+    if (active) {
+        const int64_t i = env0 + tid;
+        if (kObserve) r = env_observe(p, s, st, k, i);
+        else r = env_step<OutT>(p, s, st, k, i, actions, rewards, dones, stats != nullptr, step);
+    }
+    sh_row0[tid] = r.row0;
+    sh_pf[tid] = (OutT)r.posfeat;
+    if (!kObserve) accumulate_stats(stats, r, active);
+    __syncthreads();
+    const int lane = tid & 31, warp = tid >> 5;
+    const OutT *lr = reinterpret_cast<const OutT *>(s.logret);
+    const int nvals = W * 5;
+    for (int e = warp; e < nvalid; e += kThreads / 32) {
+        const OutT *src = lr + sh_row0[e] * 4;
+        OutT *dst = obs + (size_t)(env0 + e) * nvals;
+        const OutT pfe = sh_pf[e];
+        for (int f = lane; f < nvals; f += 32) {
+            const int j = f / 5, c = f - j * 5;
+            dst[f] = c == 4 ? pfe : __ldg(src + j * 4 + c);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// reset_all, log-returns, effective segment length
+// ------------------------------------------------------------------------------------------
+__global__ void fe_reset_all_kernel(const FeParams p, const FeSeries s, const FeState st, const uint64_t step,
+                                    const int redraw) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.num_envs) return;
+    st.cash[i] = (float)p.starting_balance;
+    st.margin[i] = 0.0;
+    st.long_sh[i] = 0.0f;
+    st.short_sh[i] = 0.0f;
+    int32_t ptr = 0;
+    if (redraw) {
+        int32_t seg;
+        draw_segment(p, s, p.env_id_base + i, step, 1u, seg, ptr);
+        st.seg[i] = seg;
+    }
+    st.ptr[i] = ptr;
+    if (st.terminated) st.terminated[i] = 0;
+    if (st.ep_return) st.ep_return[i] = 0.0f;
+    if (st.ep_len) st.ep_len[i] = 0;
+}
+
+// :179-194.  log() here is CUDA's double-precision log (<= 1 ulp), the reference's is torch's.
+__global__ void fe_log_returns_kernel(const double *__restrict__ prices, const int64_t num_rows, const int A,
+                                      double *__restrict__ lr64, float *__restrict__ lr32) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; // (t, a)
+    if (idx >= num_rows * A) return;
+    const int64_t t = idx / A;
+    const double *px = prices + idx * 4;
+    const double o = px[0];
+    const double prev_close = t == 0 ? o : prices[(idx - A) * 4 + 3];
+    double v[4];
+    v[0] = dmul(100.0, log(__ddiv_rn(o, prev_close)));
+#pragma unroll
+    for (int c = 1; c < 4; ++c) v[c] = dmul(100.0, log(__ddiv_rn(px[c], o)));
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        if (lr64) lr64[idx * 4 + c] = v[c];
+        if (lr32) lr32[idx * 4 + c] = (float)v[c];
+    }
+}
+
+// :486-496 folded into the table: one warp per segment scans for the first NaN in column 0
+__global__ void fe_effective_len_kernel(const double *__restrict__ lr64, const int64_t *__restrict__ seg_start,
+                                        const int32_t *__restrict__ raw_len, const int D, const int W, const int A,
+                                        int32_t *__restrict__ seg_len) {
+    const int d = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (d >= D) return;
+    const int64_t start = seg_start[d];
+    const int n = raw_len[d];
+    int best = n;
+    for (int kk = W + 1 + lane; kk < n; kk += 32) {
+        const double v = lr64[(size_t)(start + kk) * A * 4];
+        if (v != v) { best = kk; break; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
+    if (lane == 0) seg_len[d] = best;
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+int check_common(const FeParams *p, const FeSeries *s, const FeState *st) {
+    if (!p || !s || !st) return FE_EINVAL;
+    if (p->num_envs <= 0 || p->window <= 0 || p->num_segments <= 0 || p->num_rows <= 0) return FE_EINVAL;
+    if (p->num_assets != 1) return FE_EINVAL;
+    if (!s->prices || !s->logret || !s->seg_start || !s->seg_len) return FE_EINVAL;
+    if (!st->seg || !st->ptr || !st->cash || !st->long_sh || !st->short_sh || !st->margin) return FE_EINVAL;
+    if (p->evaluate && (!st->terminated || !st->ep_return)) return FE_EINVAL;
+    if (((uintptr_t)s->prices | (uintptr_t)s->logret) & 15) return FE_EALIGN;
+    return 0;
+}
+
+int pick_tile_envs(int W, bool f64) {
+    const size_t sz = f64 ? 8 : 4;
+    auto fit = [&](size_t budget) {
+        long e = (long)((budget - kSmemHeader - 16) / ((size_t)W * 9 * sz + sz));
+        if (e > kMaxTileEnvs) e = kMaxTileEnvs;
+        return (int)(e & ~3L); // multiple of 4 keeps every full tile's byte count a multiple of 16
+    };
+    int e = fit(kSmemTarget);
+    if (e < 8) e = fit(kSmemMax);
+    return e < 4 ? 0 : e;
+}
+
+template <typename OutT, bool kObserve>
+int launch(const FeParams &p, const FeSeries &s, const FeState &st, const float *actions, void *obs, void *rewards,
+           int32_t *dones, FeStats *stats, uint64_t step, cudaStream_t stream) {
+    const Consts k = make_consts(p);
+    int E = p.variant == FE_VARIANT_DIRECT ? 0 : pick_tile_envs(p.window, sizeof(OutT) == 8);
+    if (p.variant == FE_VARIANT_TILE && E == 0) return FE_ESMEM;
+    if (E > 0) {
+        if ((uintptr_t)obs & 15) return FE_EALIGN;
+        const size_t smem = tile_smem_bytes<OutT>(E, p.window);
+        auto kern = fe_tile_kernel<OutT, kObserve>;
+        static size_t configured[16] = {0}; // per device: largest opt-in already set for this instantiation
+        const int dev = p.device & 15;
+        if (smem > configured[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+            if (e != cudaSuccess) return (int)e;
+            configured[dev] = kSmemMax;
+        }
+        const int64_t blocks = (p.num_envs + E - 1) / E;
+        kern<<<(unsigned)blocks, kThreads, smem, stream>>>(p, s, st, k, actions, (OutT *)obs, (OutT *)rewards, dones,
+                                                           stats, step, E);
+    } else {
+        const int64_t blocks = (p.num_envs + kThreads - 1) / kThreads;
+        fe_direct_kernel<OutT, kObserve><<<(unsigned)blocks, kThreads, 0, stream>>>(
+            p, s, st, k, actions, (OutT *)obs, (OutT *)rewards, dones, stats, step);
+    }
+    return (int)cudaGetLastError();
+}
+
+int set_device(int device) {
+    int cur = -1;
+    cudaError_t e = cudaGetDevice(&cur);
+    if (e != cudaSuccess) return (int)e;
+    if (cur != device) {
+        e = cudaSetDevice(device);
+        if (e != cudaSuccess) return (int)e;
+    }
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int fe_version(void) { return FE_ABI_VERSION; }
+
+const char *fe_error_string(int code) {
+    switch (code) {
+    case 0: return "ok";
+    case FE_EINVAL: return "finenvs_b200: invalid argument (null pointer, non-positive size or num_assets != 1)";
+    case FE_EALIGN: return "finenvs_b200: pointer not 16-byte aligned";
+    case FE_ESMEM: return "finenvs_b200: window too large for the tile variant";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "finenvs_b200: unknown error";
+    }
+}
+
+int fe_tile_envs(int32_t window, int32_t out_f64, int32_t device) {
+    (void)device;
+    return window > 0 ? pick_tile_envs(window, out_f64 != 0) : 0;
+}
+
+int fe_log_returns(const double *prices_dev, int64_t num_rows, int32_t num_assets, double *logret64_dev,
+                   float *logret32_dev, void *stream) {
+    if (!prices_dev || num_rows <= 0 || num_assets <= 0) return FE_EINVAL;
+    const int64_t n = num_rows * num_assets;
+    fe_log_returns_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(prices_dev, num_rows, num_assets,
+                                                                                         logret64_dev, logret32_dev);
+    return (int)cudaGetLastError();
+}
+
+int fe_effective_len(const double *logret64_dev, const int64_t *seg_start_dev, const int32_t *raw_len_dev,
+                     int32_t num_segments, int32_t window, int32_t num_assets, int32_t *seg_len_dev, void *stream) {
+    if (!logret64_dev || !seg_start_dev || !raw_len_dev || !seg_len_dev || num_segments <= 0) return FE_EINVAL;
+    const int64_t threads = (int64_t)num_segments * 32;
+    fe_effective_len_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        logret64_dev, seg_start_dev, raw_len_dev, num_segments, window, num_assets, seg_len_dev);
+    return (int)cudaGetLastError();
+}
+
+int fe_observe(const FeParams *p, const FeSeries *s, const FeState *st, void *obs_dev, void *stream) {
+    int rc = check_common(p, s, st);
+    if (rc) return rc;
+    if (!obs_dev) return FE_EINVAL;
+    if ((rc = set_device(p->device))) return rc;
+    return p->out_f64 ? launch<double, true>(*p, *s, *st, nullptr, obs_dev, nullptr, nullptr, nullptr, 0, (cudaStream_t)stream)
+                      : launch<float, true>(*p, *s, *st, nullptr, obs_dev, nullptr, nullptr, nullptr, 0, (cudaStream_t)stream);
+}
+
+int fe_step(const FeParams *p, const FeSeries *s, const FeState *st, const float *actions_dev, void *obs_dev,
+            void *rewards_dev, int32_t *dones_dev, FeStats *stats_dev, uint64_t step_counter, void *stream) {
+    int rc = check_common(p, s, st);
+    if (rc) return rc;
+    if (!actions_dev || !obs_dev || !rewards_dev || !dones_dev) return FE_EINVAL;
+    if (stats_dev && !p->evaluate && (!st->ep_return || !st->ep_len)) return FE_EINVAL;
+    if ((rc = set_device(p->device))) return rc;
+    return p->out_f64 ? launch<double, false>(*p, *s, *st, actions_dev, obs_dev, rewards_dev, dones_dev, stats_dev,
+                                              step_counter, (cudaStream_t)stream)
+                      : launch<float, false>(*p, *s, *st, actions_dev, obs_dev, rewards_dev, dones_dev, stats_dev,
+                                             step_counter, (cudaStream_t)stream);
+}
+
+int fe_step_host(const FeParams *p, const FeSeries *s, const FeState *st, const float *actions_host, float *actions_dev,
+                 void *obs_dev, void *rewards_dev, int32_t *dones_dev, void *rewards_host, int32_t *dones_host,
+                 FeStats *stats_dev, uint64_t step_counter, void *stream) {
+    if (!p || !actions_host || !actions_dev || !rewards_host || !dones_host) return FE_EINVAL;
+    int rc = set_device(p->device);
+    if (rc) return rc;
+    cudaStream_t q = (cudaStream_t)stream;
+    const size_t n = (size_t)p->num_envs;
+    cudaError_t e = cudaMemcpyAsync(actions_dev, actions_host, n * p->num_assets * sizeof(float), cudaMemcpyHostToDevice, q);
+    if (e != cudaSuccess) return (int)e;
+    rc = fe_step(p, s, st, actions_dev, obs_dev, rewards_dev, dones_dev, stats_dev, step_counter, stream);
+    if (rc) return rc;
+    e = cudaMemcpyAsync(rewards_host, rewards_dev, n * (p->out_f64 ? 8 : 4), cudaMemcpyDeviceToHost, q);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemcpyAsync(dones_host, dones_dev, n * sizeof(int32_t), cudaMemcpyDeviceToHost, q);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaStreamSynchronize(q);
+}
+
+int fe_reset_all(const FeParams *p, const FeSeries *s, const FeState *st, uint64_t step_counter, int32_t redraw,
+                 void *stream) {
+    int rc = check_common(p, s, st);
+    if (rc) return rc;
+    if ((rc = set_device(p->device))) return rc;
+    fe_reset_all_kernel<<<(unsigned)((p->num_envs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*p, *s, *st, step_counter,
+                                                                                                 redraw);
+    return (int)cudaGetLastError();
+}
+
+void fe_philox(uint64_t seed, uint64_t env_id, uint64_t step, uint32_t kind, uint32_t out[4]) {
+    philox4x32_10(seed, env_id, step, kind, out);
+}
+
+} // extern "C"

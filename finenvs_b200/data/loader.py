@@ -1,0 +1,182 @@
+"""Series loader and one-time HBM staging.
+
+Replaces the reference's loader (finenvs/environments/time_series_env.py:80-216) with a vectorised
+pass that produces the FLAT layout the step kernel reads:
+
+    prices   (T, 4) f64   O,H,L,C of every kept bar                        (:169-177)
+    logret   (T, 4) f32|f64   100*log-returns, computed on the GPU          (:179-194)
+    seg_start (D,) i64    first row of segment d = first bar of the day - W history rows (:141-152)
+    seg_len   (D,) i32    rows of segment d, with the NaN end-of-day probe folded in (:486-496)
+
+instead of the reference's two NaN-padded, history-duplicating (D, L, 4) tensors (:196-216).  Row j
+of the reference's `*_environments[d]` is row `seg_start[d] + j` here.  The O(D*T) per-day boolean
+scans of :127-152 become one first/last-occurrence pass over the Date column.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from glob import glob
+
+import numpy as np
+import torch
+
+from .. import _lib
+
+MARKET_OPEN_S = (9 * 60 + 30) * 60   # between_time("9:30", "15:59") :90-91, both ends inclusive
+MARKET_CLOSE_S = (15 * 60 + 59) * 60
+
+PACKAGE_DATA_DIR = os.path.dirname(os.path.abspath(__file__))
+
+
+# ----------------------------------------------------------------------------- file lookup ----
+def get_data_dir_name(data_dir_name: str) -> str:
+    """:47-51 — a name containing "data" is used verbatim as a path, anything else names an
+    instrument directory under the package data dir (or $FINENVS_DATA_DIR)."""
+    if "data" not in data_dir_name:
+        base = os.environ.get("FINENVS_DATA_DIR", PACKAGE_DATA_DIR)
+        data_dir_name = os.path.join(base, data_dir_name)
+    return data_dir_name
+
+
+def determine_file_key(key_attempt: str) -> str:
+    """:53-58"""
+    possible_keys = ["dummy", "train", "valid", "test"]
+    for possible_key in possible_keys:
+        if possible_key in key_attempt:
+            return possible_key
+    raise Exception("dataset_key expected to be one of: " + str(possible_keys))
+
+
+def find_file_by_key(data_dir_name: str, key_string: str) -> str:
+    """:60-73 — exactly one `*<key>*.csv` must exist."""
+    filenames = glob(os.path.join(data_dir_name, "*" + key_string + "*.csv"))
+    if len(filenames) == 0:
+        raise Exception(f"No file was found in {data_dir_name} with key ({key_string})")
+    if len(filenames) > 1:
+        raise Exception(f"More than one file was found in {data_dir_name} with key ({key_string})")
+    return filenames[0]
+
+
+# ----------------------------------------------------------------------------- host tables ----
+@dataclass
+class HostSeries:
+    prices: np.ndarray       # (T, 4) f64
+    seg_start: np.ndarray    # (D,) i64
+    seg_len_raw: np.ndarray  # (D,) i32 = W + bars of the day
+
+
+def _seconds_of_day(times) -> np.ndarray:
+    parts = times.astype(str).str.split(":", expand=True)
+    secs = parts[0].astype(np.int64) * 3600 + parts[1].astype(np.int64) * 60
+    if parts.shape[1] > 2:
+        secs = secs + parts[2].fillna(0).astype(float).astype(np.int64)
+    return secs.to_numpy()
+
+
+def segment_table(dates: np.ndarray, window: int):
+    """First/last row of every distinct Date (:141-152), backtracked by W rows of history; days
+    whose history would start before row 0 are skipped (:134).  Order = first appearance."""
+    codes, first, inv = np.unique(dates, return_index=True, return_inverse=True)
+    last = np.zeros(len(codes), dtype=np.int64)
+    np.maximum.at(last, inv, np.arange(len(dates), dtype=np.int64))
+    order = np.argsort(first, kind="stable")
+    first, last = first[order].astype(np.int64), last[order]
+    start = first - window
+    keep = start >= 0
+    return start[keep], (last[keep] - start[keep] + 1).astype(np.int32)
+
+
+def read_market_csv(path: str, window: int) -> HostSeries:
+    """read_data :80-88 + force_market_hours :90-91 + determine_environment_bounds :127-152."""
+    import pandas as pd
+
+    df = pd.read_csv(path, names=["Date", "Time", "Open", "High", "Low", "Close", "Volume"])
+    secs = _seconds_of_day(df["Time"])
+    keep = (secs >= MARKET_OPEN_S) & (secs <= MARKET_CLOSE_S)
+    df = df[keep]
+    prices = np.ascontiguousarray(df[["Open", "High", "Low", "Close"]].to_numpy(dtype=np.float64))
+    seg_start, seg_len_raw = segment_table(df["Date"].to_numpy().astype(str), window)
+    if len(seg_start) == 0:
+        raise Exception(f"{path}: no trading day has {window} bars of history before it")
+    return HostSeries(prices, seg_start, seg_len_raw)
+
+
+def regular_segments(num_rows: int, bars_per_segment: int, window: int):
+    """Segment table for a synthetic series cut into equal days (BASELINE configs 2-5)."""
+    firsts = np.arange(0, num_rows - bars_per_segment + 1, bars_per_segment, dtype=np.int64)
+    start = firsts - window
+    keep = start >= 0
+    start = start[keep]
+    return start, np.full(len(start), window + bars_per_segment, dtype=np.int32)
+
+
+# ---------------------------------------------------------------------------------- staging ----
+@dataclass
+class StagedSeries:
+    """The series resident in HBM (device tensors) + the small host-side facts about it."""
+
+    prices: torch.Tensor      # (T, 4) f64
+    logret: torch.Tensor      # (T, 4) f32 or f64 (matches the observation dtype)
+    seg_start: torch.Tensor   # (D,) i64
+    seg_len: torch.Tensor     # (D,) i32 effective
+    seg_len_raw: torch.Tensor  # (D,) i32
+    window: int
+    logret64: torch.Tensor | None = None  # kept only when asked (loader parity tests)
+
+    @property
+    def num_rows(self) -> int:
+        return int(self.prices.shape[0])
+
+    @property
+    def num_segments(self) -> int:
+        return int(self.seg_start.shape[0])
+
+    @property
+    def device(self) -> torch.device:
+        return self.prices.device
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in (self.prices, self.logret, self.seg_start, self.seg_len))
+
+
+def stage_series(prices, seg_start, seg_len_raw, window: int, device: str, obs_dtype=torch.float32,
+                 keep_logret64: bool = False) -> StagedSeries:
+    """Upload OHLC once (pinned staging buffer -> HBM), derive log-returns and the effective segment
+    lengths on the GPU (fe_log_returns / fe_effective_len)."""
+    L = _lib.lib()
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("stage_series needs a CUDA device (no CPU path)")
+    prices_h = torch.as_tensor(np.ascontiguousarray(prices, dtype=np.float64)) if not torch.is_tensor(prices) else prices
+    if prices_h.dim() != 2 or prices_h.shape[1] != 4:
+        raise ValueError(f"prices must be (T, 4) O,H,L,C; got {tuple(prices_h.shape)}")
+    T = int(prices_h.shape[0])
+    seg_start_h = torch.as_tensor(np.ascontiguousarray(seg_start, dtype=np.int64))
+    raw_h = torch.as_tensor(np.ascontiguousarray(seg_len_raw, dtype=np.int32))
+    if seg_start_h.numel() == 0:
+        raise ValueError("empty segment table")
+    if int(seg_start_h.min()) < 0 or int((seg_start_h + raw_h.long()).max()) > T:
+        raise ValueError("segment table reaches outside the series")
+    if int(raw_h.min()) < window + 1:
+        raise ValueError("every segment needs W history rows plus at least one bar")
+    with torch.cuda.device(dev):
+        if prices_h.device.type == "cpu":
+            prices_d = prices_h.to(torch.float64).contiguous().pin_memory().to(dev, non_blocking=True)
+        else:
+            prices_d = prices_h.to(dev, torch.float64).contiguous()
+        seg_start_d = seg_start_h.to(dev)
+        raw_d = raw_h.to(dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        lr64 = torch.empty((T, 4), dtype=torch.float64, device=dev)
+        want32 = obs_dtype == torch.float32
+        lr32 = torch.empty((T, 4), dtype=torch.float32, device=dev) if want32 else None
+        _lib.check(L.fe_log_returns(prices_d.data_ptr(), T, 1, lr64.data_ptr(), lr32.data_ptr() if want32 else None,
+                                    stream), "fe_log_returns")
+        seg_len_d = torch.empty_like(raw_d)
+        _lib.check(L.fe_effective_len(lr64.data_ptr(), seg_start_d.data_ptr(), raw_d.data_ptr(), raw_d.numel(), window, 1,
+                                      seg_len_d.data_ptr(), stream), "fe_effective_len")
+        torch.cuda.current_stream(dev).synchronize()
+    logret = lr32 if want32 else lr64
+    return StagedSeries(prices_d, logret, seg_start_d, seg_len_d, raw_d, window,
+                        lr64 if (keep_logret64 or not want32) else None)

@@ -1,0 +1,346 @@
+"""TimeSeriesEnv — drop-in for the reference's finenvs/environments/time_series_env.py:14-536.
+
+Same constructor arguments, attributes and `reset()` / `step(actions)` / `get_env_args()` contract
+(torch tensors in and out, so finenvs/agents run unchanged), but the series is staged once into
+HBM as a flat table and every `step` is ONE launch of the sm_100a kernel in csrc/fe_step.cu,
+reached through the C ABI of include/finenvs_b200.h.  There is no CPU path.
+
+Keyword-only arguments after `device_id` are extensions; their defaults
+reproduce the reference's behaviour, except `obs_dtype` (float32; pass torch.float64 for the
+reference's dtype) and the redraw RNG (counter-based Philox instead of torch's global generator).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..base_object import BaseObject
+from ..data import loader
+from ..device_utils import require_cuda_device
+
+try:  # gym is metadata only (:218-234); the reference needs it, we do not
+    from gym import spaces as _spaces
+except Exception:  # pragma: no cover - gym is not installed in the target image
+    class _Box:
+        def __init__(self, low, high, shape=None, dtype=None):
+            self.low, self.high, self.dtype = low, high, dtype
+            self.shape = shape if shape is not None else np.shape(low)
+
+    class _spaces:  # type: ignore
+        Box = _Box
+
+_RESET_MODES = {"keep": _lib.RESET_KEEP, "last": _lib.RESET_LAST, "all": _lib.RESET_ALL}
+_VARIANTS = {"auto": _lib.VARIANT_AUTO, "tile": _lib.VARIANT_TILE, "direct": _lib.VARIANT_DIRECT}
+
+
+class TimeSeriesEnv(BaseObject):
+    def __init__(
+        self,
+        instrument_name: str,
+        dataset_key: str = "dummy",
+        num_intervals: int = 390,
+        max_shares: int = 5,
+        starting_balance: float = 10000,
+        per_share_commission: float = 0.01,
+        initial_margin_requirement: float = 1.5,
+        maintenance_margin_requirement: float = 0.25,
+        evaluate: bool = False,
+        device_id: int = 0,
+        *,
+        num_envs: Optional[int] = None,
+        obs_dtype: torch.dtype = torch.float32,
+        seed: Optional[int] = None,
+        random_reset: Optional[str] = None,
+        random_offset: bool = False,
+        series: Optional[loader.StagedSeries] = None,
+        env_id_base: int = 0,
+        total_envs: Optional[int] = None,
+        track_stats: bool = False,
+        variant: str = "auto",
+    ):
+        """Reference arguments: :15-29.  Extensions:
+
+        num_envs      envs on this device (default: one per trading day, +1 evaluation env when
+                      training, :246-257).  Env i starts on segment (global id) mod D.
+        obs_dtype     torch.float32 (default) or torch.float64 (reference dtype) for obs and rewards.
+        seed          Philox key of the segment redraws; default torch.initial_seed().
+        random_reset  "last" (reference training: only the last env redraws its day, :504-513),
+                      "keep" (reference evaluate: same day again), "all" (every finished env redraws).
+        random_offset redraws also draw the start offset inside the segment.
+        series        an already staged series (share one copy between envs / skip the CSV).
+        env_id_base, total_envs   this env object is a shard [base, base+num_envs) of a global
+                      population (multi-GPU); draws are keyed by global id, so results do not
+                      depend on the sharding.
+        track_stats   accumulate episode count / return / length on the device (stats()).
+        variant       "auto" | "tile" | "direct" kernel variant.
+        """
+        if obs_dtype not in (torch.float32, torch.float64):
+            raise ValueError("obs_dtype must be torch.float32 or torch.float64")
+        self.instrument_name = instrument_name
+        self.num_intervals = int(num_intervals)
+        self.max_shares = max_shares
+        self.starting_balance = starting_balance
+        self.per_share_commission = per_share_commission
+        self.initial_margin_requirement = initial_margin_requirement
+        self.maintenance_margin_requirement = maintenance_margin_requirement
+        self.log_return_scale_factor = 100
+        self.evaluate = evaluate
+        self.obs_dtype = obs_dtype
+        self.device = require_cuda_device(device_id)
+        self._dev = torch.device(self.device)
+        self._L = _lib.lib()
+        if series is None:
+            self.data_dir_name = loader.get_data_dir_name(instrument_name)
+            self.file_key = loader.determine_file_key(dataset_key)
+            self.filename = loader.find_file_by_key(self.data_dir_name, self.file_key)
+            host = loader.read_market_csv(self.filename, self.num_intervals)
+            series = loader.stage_series(host.prices, host.seg_start, host.seg_len_raw, self.num_intervals,
+                                         self.device, obs_dtype)
+        else:
+            if series.window != self.num_intervals:
+                raise ValueError(f"series was staged for W={series.window}, env asks W={self.num_intervals}")
+            if series.device != self._dev:
+                raise ValueError(f"series lives on {series.device}, env on {self._dev}")
+            if series.logret.dtype != obs_dtype:
+                raise ValueError(f"series log-returns are {series.logret.dtype}, obs_dtype is {obs_dtype}")
+        self.series = series
+        self.values_per_interval = 4
+        self.set_spaces()
+        if random_reset is None:
+            random_reset = "keep" if evaluate else "last"
+        if random_reset not in _RESET_MODES:
+            raise ValueError(f"random_reset must be one of {sorted(_RESET_MODES)}")
+        self.random_reset = random_reset
+        self.random_offset = bool(random_offset)
+        self.seed = int(torch.initial_seed() if seed is None else seed) & 0xFFFFFFFFFFFFFFFF
+        self.track_stats = bool(track_stats)
+        self.set_environment_params(num_envs, env_id_base, total_envs, _VARIANTS[variant])
+
+    # ------------------------------------------------------------------ metadata (:218-243) ----
+    def set_spaces(self) -> None:
+        self.num_obs = self.values_per_interval + 1
+        self.num_acts = 1
+        self.action_space = _spaces.Box(np.ones(self.num_acts) * -1.0, np.ones(self.num_acts) * +1.0, dtype=np.float64)
+        self.observation_space = _spaces.Box(
+            np.ones((self.num_intervals, self.num_obs)) * -np.inf,
+            np.ones((self.num_intervals, self.num_obs)) * +np.inf,
+            dtype=np.float64,
+        )
+
+    def get_env_args(self) -> Dict:
+        return {
+            "env_name": self.instrument_name,
+            "num_envs": self.num_envs,
+            "num_observations": self.num_obs,
+            "num_actions": self.num_acts,
+            "sequence_length": self.num_intervals,
+        }
+
+    # ------------------------------------------------------------------ state (:245-275) -------
+    def set_environment_params(self, num_envs=None, env_id_base=0, total_envs=None, variant=0) -> None:
+        D = self.series.num_segments
+        if num_envs is None:
+            num_envs = D if self.evaluate else D + 1  # :246-257
+        N = int(num_envs)
+        if N <= 0:
+            raise ValueError("num_envs must be positive")
+        total = int(N if total_envs is None else total_envs)
+        base = int(env_id_base)
+        if base < 0 or base + N > total:
+            raise ValueError("shard [env_id_base, env_id_base+num_envs) must lie inside total_envs")
+        self.num_envs, self.env_id_base, self.total_envs = N, base, total
+        dev = self._dev
+        gid = torch.arange(base, base + N, device=dev, dtype=torch.int64)
+        self._seg = (gid % D).to(torch.int32)
+        self._ptr = torch.zeros(N, dtype=torch.int32, device=dev)
+        self._cash = torch.full((N,), float(self.starting_balance), dtype=torch.float32, device=dev)
+        self._long = torch.zeros(N, dtype=torch.float32, device=dev)
+        self._short = torch.zeros(N, dtype=torch.float32, device=dev)
+        self._margin = torch.zeros(N, dtype=torch.float64, device=dev)
+        need_ep = self.evaluate or self.track_stats
+        self._terminated = torch.zeros(N, dtype=torch.uint8, device=dev) if self.evaluate else None
+        self._ep_return = torch.zeros(N, dtype=torch.float32, device=dev) if need_ep else None
+        self._ep_len = torch.zeros(N, dtype=torch.int32, device=dev) if self.track_stats else None
+        self._stats = torch.zeros(_lib.STATS_BYTES // 8, dtype=torch.int64, device=dev) if need_ep else None
+        self.step_count = 0
+        self._params = _lib.FeParams(
+            N, base, total, self.series.num_rows, self.num_intervals, D, 1, int(self.max_shares),
+            float(self.starting_balance), float(self.per_share_commission), float(self.initial_margin_requirement),
+            float(self.maintenance_margin_requirement), self.seed, _RESET_MODES[self.random_reset],
+            int(self.random_offset), int(self.evaluate), int(self.obs_dtype == torch.float64), variant,
+            dev.index if dev.index is not None else torch.cuda.current_device(),
+        )
+        s = self.series
+        self._cseries = _lib.FeSeries(s.prices.data_ptr(), s.logret.data_ptr(), s.seg_start.data_ptr(), s.seg_len.data_ptr())
+        self._cstate = _lib.FeState(
+            self._seg.data_ptr(), self._ptr.data_ptr(), self._cash.data_ptr(), self._long.data_ptr(),
+            self._short.data_ptr(), self._margin.data_ptr(),
+            self._terminated.data_ptr() if self._terminated is not None else None,
+            self._ep_return.data_ptr() if self._ep_return is not None else None,
+            self._ep_len.data_ptr() if self._ep_len is not None else None,
+        )
+        self._pp, self._ps, self._pst = C.byref(self._params), C.byref(self._cseries), C.byref(self._cstate)
+        if self.random_reset == "last" and base + N == total:
+            # :253-257 the extra (evaluation) env starts on a drawn day
+            r = _lib.philox(self.seed, total - 1, 0, 1)
+            self._seg[-1] = (r[0] * D) >> 32
+        elif self.random_reset == "all":
+            self._launch_reset_all(redraw=True)
+
+    def reset_evaluation_metrics(self) -> None:
+        """:271-275"""
+        self._terminated.zero_()
+        self._ep_return = torch.zeros_like(self._ep_return)
+        self._cstate.ep_return = self._ep_return.data_ptr()
+        self._stats.zero_()
+
+    # reference-named views of the state (same memory; reference shapes (N,1) / (N,))
+    @property
+    def env_indices(self) -> torch.Tensor:
+        return self._seg.long()
+
+    @property
+    def env_pointers(self) -> torch.Tensor:
+        return self._ptr.long()
+
+    @property
+    def env_spots(self) -> torch.Tensor:
+        """(N, W) row indices of the window; the reference stores this tensor (:261), here it is derived."""
+        return self._ptr.long().unsqueeze(1) + torch.arange(self.num_intervals, device=self._dev)
+
+    @property
+    def cash(self) -> torch.Tensor:
+        return self._cash.view(-1, 1)
+
+    @property
+    def long_shares(self) -> torch.Tensor:
+        return self._long.view(-1, 1)
+
+    @property
+    def short_shares(self) -> torch.Tensor:
+        return self._short.view(-1, 1)
+
+    @property
+    def margin(self) -> torch.Tensor:
+        return self._margin.view(-1, 1)
+
+    @property
+    def terminated_episodes(self) -> torch.Tensor:
+        return self._terminated.bool()
+
+    @property
+    def episode_returns(self) -> torch.Tensor:
+        return self._ep_return
+
+    # ------------------------------------------------------------------ the hot path ------------
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self._dev).cuda_stream
+
+    def _new_obs(self) -> torch.Tensor:
+        # a fresh tensor every call: the PPO buffer keeps references to past observations (buffer.py:44-56)
+        return torch.empty((self.num_envs, self.num_intervals, self.num_obs), dtype=self.obs_dtype, device=self._dev)
+
+    def reset(self) -> torch.Tensor:
+        """:423-435 — materialises the current observation; touches no state (reference semantics)."""
+        obs = self._new_obs()
+        _lib.check(self._L.fe_observe(self._pp, self._ps, self._pst, obs.data_ptr(), self._stream()), "fe_observe")
+        return obs
+
+    def _prepare_actions(self, actions: torch.Tensor) -> torch.Tensor:
+        if not torch.is_tensor(actions):
+            raise TypeError("actions must be a torch.Tensor")
+        if actions.numel() != self.num_envs:
+            raise ValueError(f"actions must have {self.num_envs} elements (num_envs, 1); got {tuple(actions.shape)}")
+        if actions.device != self._dev or actions.dtype != torch.float32 or not actions.is_contiguous():
+            actions = actions.to(device=self._dev, dtype=torch.float32, non_blocking=True).contiguous()
+        return actions
+
+    def step(self, actions: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, dict]:
+        """:277-296 — one kernel launch, no host synchronisation in training mode."""
+        actions = self._prepare_actions(actions)
+        obs = self._new_obs()
+        rewards = torch.empty(self.num_envs, dtype=self.obs_dtype, device=self._dev)
+        dones = torch.empty(self.num_envs, dtype=torch.int32, device=self._dev)
+        self.step_into(actions, obs, rewards, dones)
+        info_dict = self.record_evaluation_metrics() if self.evaluate else {}
+        return (obs, rewards, dones, info_dict)
+
+    def step_into(self, actions: torch.Tensor, obs: torch.Tensor, rewards: torch.Tensor, dones: torch.Tensor) -> None:
+        """step() into caller-owned output tensors (zero allocation; CUDA-graph capturable)."""
+        self.step_count += 1
+        _lib.check(
+            self._L.fe_step(self._pp, self._ps, self._pst, actions.data_ptr(), obs.data_ptr(), rewards.data_ptr(),
+                            dones.data_ptr(), self._stats.data_ptr() if self._stats is not None else None,
+                            self.step_count, self._stream()),
+            "fe_step",
+        )
+
+    def step_host(self, actions_host: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, dict]:
+        """step() for a host-resident policy, through fe_step_host: `actions_host` is a CPU tensor
+        (pinned for full speed); rewards and dones come back as pinned CPU tensors, already complete when the
+        call returns (the two pinned buffers are reused by the next step_host call; copy them to keep them);
+        the observation stays in HBM.  Per step: 4N bytes host->device, 8N (f32) device->host."""
+        if actions_host.device.type != "cpu" or actions_host.dtype != torch.float32 or not actions_host.is_contiguous():
+            raise ValueError("actions_host must be a contiguous float32 CPU tensor")
+        if actions_host.numel() != self.num_envs:
+            raise ValueError(f"actions must have {self.num_envs} elements")
+        if not hasattr(self, "_host_bufs"):
+            self._host_bufs = (
+                torch.empty(self.num_envs, dtype=torch.float32, device=self._dev),
+                torch.empty(self.num_envs, dtype=self.obs_dtype, device=self._dev),
+                torch.empty(self.num_envs, dtype=torch.int32, device=self._dev),
+                torch.empty(self.num_envs, dtype=self.obs_dtype).pin_memory(),
+                torch.empty(self.num_envs, dtype=torch.int32).pin_memory(),
+            )
+        a_dev, r_dev, d_dev, rewards, dones = self._host_bufs
+        obs = self._new_obs()
+        self.step_count += 1
+        _lib.check(
+            self._L.fe_step_host(self._pp, self._ps, self._pst, actions_host.data_ptr(), a_dev.data_ptr(), obs.data_ptr(),
+                                 r_dev.data_ptr(), d_dev.data_ptr(), rewards.data_ptr(), dones.data_ptr(),
+                                 self._stats.data_ptr() if self._stats is not None else None, self.step_count,
+                                 self._stream()),
+            "fe_step_host",
+        )
+        info_dict = self.record_evaluation_metrics() if self.evaluate else {}
+        return (obs, rewards, dones, info_dict)
+
+    def record_evaluation_metrics(self) -> Dict:
+        """:523-536 — the per-env bookkeeping ran inside the kernel; here only the "all terminated"
+        test (:531), which like the reference's torch.all() costs one host read per step."""
+        n_terminated = int(self._stats[1].item())
+        if n_terminated >= self.num_envs:
+            info_dict = {"returns": self._ep_return}
+            self.reset_evaluation_metrics()
+            return info_dict
+        return {}
+
+    # ------------------------------------------------------------------ extensions --------------
+    def _launch_reset_all(self, redraw: bool) -> None:
+        _lib.check(self._L.fe_reset_all(self._pp, self._ps, self._pst, self.step_count, int(redraw), self._stream()),
+                   "fe_reset_all")
+
+    def reset_all(self, redraw: Optional[bool] = None) -> torch.Tensor:
+        """Fresh episode for every env (the reset the ES loop expects, cf. isaac_gym_env.py:55-58)."""
+        if redraw is None:
+            redraw = self.random_reset == "all"
+        self._launch_reset_all(redraw)
+        if self._stats is not None:
+            self._stats.zero_()
+        return self.reset()
+
+    def stats(self) -> Dict[str, torch.Tensor]:
+        """Device-side episode statistics accumulated since the last clear (track_stats=True)."""
+        if self._stats is None:
+            raise RuntimeError("construct the env with track_stats=True")
+        f = self._stats.view(torch.float64)
+        return {"n_done": self._stats[0], "n_terminated": self._stats[1], "sum_len": self._stats[2],
+                "sum_return": f[4], "sum_return_sq": f[5]}
+
+    def clear_stats(self) -> None:
+        if self._stats is not None:
+            self._stats.zero_()

@@ -1,0 +1,143 @@
+/*
+ * finenvs_b200.h — C ABI of the B200-native trading-env step.
+ *
+ * The reference (hmomin/FinEnvs) has no native layer: its hot path is ~660 torch-eager ops inside
+ * finenvs/environments/time_series_env.py.  Each entry point below replaces the reference METHOD(s)
+ * named in its comment (file = finenvs/environments/time_series_env.py); the Python class
+ * finenvs_b200.environments.TimeSeriesEnv binds them with ctypes and keeps the reference's
+ * reset()/step() surface.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch / C++ types; every `*_dev` / struct pointer member is a DEVICE
+ *     pointer owned by the caller (the library allocates nothing persistent and frees nothing);
+ *   - `stream` is a cudaStream_t (CUstream) passed as void*; calls only enqueue work and never
+ *     synchronise, except fe_step_host which returns after its device->host copies completed;
+ *   - return 0 on success, a negative FE_E* code for a rejected argument, or a positive cudaError_t;
+ *   - no exceptions cross the boundary; there is NO CPU fallback: without a CUDA device every compute
+ *     entry point returns a cudaError.
+ */
+#ifndef FINENVS_B200_H
+#define FINENVS_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FE_ABI_VERSION 1
+
+/* argument errors */
+#define FE_EINVAL (-1)   /* null pointer / non-positive size / unsupported num_assets */
+#define FE_EALIGN (-2)   /* pointer not 16-byte aligned */
+#define FE_ESMEM (-3)    /* window too large for the requested kernel variant */
+
+/* FeParams.reset_mode */
+#define FE_RESET_KEEP 0  /* finished envs restart on the same segment (reference evaluate=True, :504) */
+#define FE_RESET_LAST 1  /* only the globally-last env redraws its segment (reference training mode, :504-513) */
+#define FE_RESET_ALL 2   /* extension: every finished env redraws its segment */
+
+/* FeParams.variant */
+#define FE_VARIANT_AUTO 0   /* bulk-copy (TMA) tile kernel when the window fits in shared memory, else direct */
+#define FE_VARIANT_TILE 1   /* cp.async.bulk in -> smem interleave -> cp.async.bulk out */
+#define FE_VARIANT_DIRECT 2 /* warp-per-env global->global copy (any window) */
+
+typedef struct FeParams {
+    int64_t num_envs;        /* envs held by this GPU (a shard) */
+    int64_t env_id_base;     /* global id of local env 0 (keys the redraw RNG; results do not depend on sharding) */
+    int64_t total_envs;      /* global env count; the reference's evaluation env is id total_envs-1 (:250-257) */
+    int64_t num_rows;        /* T: rows of the flat series */
+    int32_t window;          /* W = num_intervals (:19) */
+    int32_t num_segments;    /* D: trading days / segments */
+    int32_t num_assets;      /* A: 1 for the reference env */
+    int32_t max_shares;      /* :20 */
+    double starting_balance; /* :21 */
+    double commission;       /* per_share_commission :22 */
+    double imr;              /* initial_margin_requirement :25 */
+    double mmr;              /* maintenance_margin_requirement :26 */
+    uint64_t seed;           /* Philox key for segment / offset redraws */
+    int32_t reset_mode;      /* FE_RESET_* */
+    int32_t random_offset;   /* extension: a redraw also draws the start offset inside the segment */
+    int32_t evaluate;        /* reference evaluate=True (:523-536): needs state.terminated / ep_return */
+    int32_t out_f64;         /* 1: obs/rewards are double (reference dtype); 0: float */
+    int32_t variant;         /* FE_VARIANT_* */
+    int32_t device;          /* CUDA device ordinal the pointers live on */
+} FeParams;
+
+/* Series staged once into HBM (replaces the two NaN-padded (D,L,4) tensors of :196-216). */
+typedef struct FeSeries {
+    const double *prices;     /* (T, A, 4) f64 O,H,L,C            (:169-177) */
+    const void *logret;       /* (T, A, 4) 100*log-returns, float when !out_f64 else double (:179-194) */
+    const int64_t *seg_start; /* (D,) first row of segment d: first bar of the day minus W history rows (:141-152) */
+    const int32_t *seg_len;   /* (D,) rows in segment d with the NaN probe of :486-496 folded in */
+} FeSeries;
+
+/* Per-env state, structure of arrays (replaces the tensors of :245-275). */
+typedef struct FeState {
+    int32_t *seg;        /* (N,)   env -> segment            (env_indices :246) */
+    int32_t *ptr;        /* (N,)   time pointer              (env_pointers :258; env_spots[i,j] == ptr[i]+j) */
+    float *cash;         /* (N,)   :264 */
+    float *long_sh;      /* (N,A)  :267 */
+    float *short_sh;     /* (N,A)  :268 */
+    double *margin;      /* (N,A)  :269 (f64 from the first step on, :383) */
+    uint8_t *terminated; /* (N,)   evaluate only :272 (may be NULL otherwise) */
+    float *ep_return;    /* (N,)   evaluate: :275; training: running episode return when stats != NULL */
+    int32_t *ep_len;     /* (N,)   running episode length when stats != NULL (may be NULL) */
+} FeState;
+
+/* Device-side episode statistics, accumulated with one atomic per thread block (extension; the
+ * values all-reduced over NCCL by finenvs_b200.parallel).  May be NULL. */
+typedef struct FeStats {
+    unsigned long long n_done;       /* envs finished (all steps since last clear) */
+    unsigned long long n_terminated; /* evaluate: envs terminated since the metrics were reset (:529-531) */
+    unsigned long long sum_len;      /* sum of finished episode lengths */
+    unsigned long long pad;
+    double sum_return;               /* sum of finished episode returns */
+    double sum_return_sq;
+} FeStats;
+
+int fe_version(void);
+const char *fe_error_string(int code);
+
+/* Shared-memory bytes per env the tile variant needs for (window, out_f64), and the envs-per-block it
+ * would pick (0 = does not fit, the direct variant is used). */
+int fe_tile_envs(int32_t window, int32_t out_f64, int32_t device);
+
+/* generate_log_return_dataset (:179-194): logret[t,a,0] = 100*log(O_t/C_{t-1}) (row 0: O_0/O_0),
+ * logret[t,a,1..3] = 100*log(H|L|C / O).  Either output may be NULL. */
+int fe_log_returns(const double *prices_dev, int64_t num_rows, int32_t num_assets, double *logret64_dev,
+                   float *logret32_dev, void *stream);
+
+/* find_nan_spots (:486-496) folded into the segment table:
+ * seg_len[d] = min(raw_len[d], first k >= W+1 with isnan(logret64[seg_start[d]+k, 0, 0])). */
+int fe_effective_len(const double *logret64_dev, const int64_t *seg_start_dev, const int32_t *raw_len_dev,
+                     int32_t num_segments, int32_t window, int32_t num_assets, int32_t *seg_len_dev, void *stream);
+
+/* reset() (:423-445): materialise the current observation (N, W, 5A); touches no state. */
+int fe_observe(const FeParams *p, const FeSeries *s, const FeState *st, void *obs_dev, void *stream);
+
+/* step() (:277-296) and everything it calls (:298-536) as ONE kernel.
+ * actions (N,A) float in [-1,1]; obs (N,W,5A); rewards (N,); dones (N,) int32.
+ * step_counter: ordinal of this step (1 for the first step after construction / reset_all). */
+int fe_step(const FeParams *p, const FeSeries *s, const FeState *st, const float *actions_dev, void *obs_dev,
+            void *rewards_dev, int32_t *dones_dev, FeStats *stats_dev, uint64_t step_counter, void *stream);
+
+/* Same step driven from HOST buffers (the call a non-torch embedder makes): copies actions host->device,
+ * runs fe_step, copies rewards and dones device->host and waits for them.  The observation stays in HBM
+ * (obs_dev) for the policy.  actions_host/rewards_host/dones_host should be pinned for full speed. */
+int fe_step_host(const FeParams *p, const FeSeries *s, const FeState *st, const float *actions_host,
+                 float *actions_dev, void *obs_dev, void *rewards_dev, int32_t *dones_dev, void *rewards_host,
+                 int32_t *dones_host, FeStats *stats_dev, uint64_t step_counter, void *stream);
+
+/* Extension (mirrors isaac_gym_env.py:55-58 reset_all): fresh episode for every env; with redraw != 0
+ * each env draws (segment[, offset]) from Philox(seed, global env id, step_counter). */
+int fe_reset_all(const FeParams *p, const FeSeries *s, const FeState *st, uint64_t step_counter, int32_t redraw,
+                 void *stream);
+
+/* The redraw RNG evaluated on the host (Philox4x32-10; key = seed, counter = (env id, step, kind)):
+ * lets callers reproduce / pre-compute draws.  kind: 0 step-time reset, 1 reset_all / constructor. */
+void fe_philox(uint64_t seed, uint64_t env_id, uint64_t step, uint32_t kind, uint32_t out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FINENVS_B200_H */

@@ -109,3 +109,41 @@ def replay_trace(z, env, get_state, out_f64: bool, name: str = ""):
         assert bool(info) == (t in info_steps), f"{name} info presence t={t}"
         if info:
             assert_bits_equal(z["info_returns"][info_steps[t]], np.asarray(info["returns"]), f"{name} returns t={t}")
+
+
+# ------------------------------------------------------------------ CUDA env adapter --------
+class CudaAdapter:
+    """Drives finenvs_b200.TimeSeriesEnv with numpy in/out so replay_trace / lock-step loops can
+    treat it like the oracle."""
+
+    def __init__(self, env):
+        self.env = env
+
+    def reset(self):
+        return self.env.reset().cpu().numpy()
+
+    def step(self, actions):
+        import torch
+
+        a = torch.from_numpy(np.ascontiguousarray(actions, dtype=np.float32)).view(-1, 1).to(self.env.device)
+        o, r, d, info = self.env.step(a)
+        return o.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy(), {k: v.cpu().numpy() for k, v in info.items()}
+
+    def state(self):
+        e = self.env
+        return {
+            "seg": e._seg.cpu().numpy(), "ptr": e._ptr.cpu().numpy(), "cash": e._cash.cpu().numpy(),
+            "long_sh": e._long.cpu().numpy(), "short_sh": e._short.cpu().numpy(), "margin": e._margin.cpu().numpy(),
+        }
+
+
+def stage_trace_series(z, dtype, device="cuda:0"):
+    """Stage a golden trace's series; the log-returns are overwritten with the reference's own values
+    (torch.log on CPU) so observations can be compared bit-for-bit; fe_log_returns is tested apart."""
+    import torch
+    from finenvs_b200.data import loader
+
+    s = loader.stage_series(z["prices"], z["seg_start"], z["seg_len_raw"], int(z["window"]), device, dtype,
+                            keep_logret64=True)
+    s.logret.copy_(torch.from_numpy(z["logret"]).to(dtype))
+    return s

@@ -1,0 +1,99 @@
+"""The C-ABI library loads and exports every symbol include/finenvs_b200.h declares (no compute
+calls: this runs without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from parity_utils import ROOT
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as ge
+
+    ge.build()
+    from finenvs_b200 import _lib
+
+    return _lib
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "finenvs_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(fe_[a-z_0-9]+)\s*\(", hdr)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(built):
+    names = _declared_symbols()
+    assert len(names) >= 10
+    raw = ctypes.CDLL(built.LIB_PATH)
+    for n in names:
+        assert hasattr(raw, n), f"{n} declared in the header but not exported"
+    assert sorted(built.EXPORTS) == names, "ctypes binding and header disagree"
+    assert built.lib().fe_version() == built.ABI_VERSION
+
+
+def test_struct_layouts_match_the_header(built):
+    # sizes implied by the header's field lists (LP64): a silent mismatch would corrupt every call
+    assert ctypes.sizeof(built.FeParams) == 4 * 8 + 4 * 4 + 4 * 8 + 8 + 6 * 4
+    assert ctypes.sizeof(built.FeSeries) == 4 * 8
+    assert ctypes.sizeof(built.FeState) == 9 * 8
+    assert built.STATS_BYTES == 6 * 8
+
+
+def test_error_strings_and_argument_validation(built):
+    L = built.lib()
+    assert L.fe_error_string(0) == b"ok"
+    assert b"invalid" in L.fe_error_string(-1)
+    assert b"aligned" in L.fe_error_string(-2)
+    # null params are rejected before any CUDA call is made
+    assert L.fe_step(None, None, None, None, None, None, None, None, 1, None) == -1
+    assert L.fe_observe(None, None, None, None, None) == -1
+    assert L.fe_log_returns(None, 0, 1, None, None, None) == -1
+
+
+def test_host_philox_matches_oracle_and_known_answer(built):
+    from oracle import oracle as orc
+
+    # Philox4x32-10 known answer (Random123 kat_vectors): ctr=0, key=0
+    assert built.philox(0, 0, 0, 0) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        seed, env, step = (int(x) for x in rng.integers(0, 2**63 - 1, 3))
+        kind = int(rng.integers(0, 2))
+        assert built.philox(seed, env, step, kind) == [int(x) for x in orc.philox(seed, env, step, kind)]
+
+
+def test_tile_sizes(built):
+    L = built.lib()
+    assert L.fe_tile_envs(60, 0, 0) == 32      # 32 envs x 60 rows x 36 B = 69 KB -> 3 blocks / SM
+    assert L.fe_tile_envs(60, 1, 0) == 16
+    assert L.fe_tile_envs(390, 0, 0) == 16     # the reference default window
+    assert L.fe_tile_envs(128, 0, 0) % 4 == 0
+    assert L.fe_tile_envs(2000, 0, 0) == 0     # falls back to the direct variant
+    assert L.fe_tile_envs(0, 0, 0) == 0
+
+
+def test_env_has_no_cpu_fallback(built):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from finenvs_b200.environments import TimeSeriesEnv
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        TimeSeriesEnv("IBM", "dummy")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        TimeSeriesEnv("IBM", "dummy", device_id=-1)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "finenvs_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("# oracle", ""), f"{f} mentions the oracle"

@@ -1,0 +1,258 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the golden traces the
+reference produced and against the CPU oracle on seeded inputs.  Bit-exact everywhere: integers by
+construction, floats because the kernel performs the reference's IEEE operations in the reference's
+order (the stated tolerance of 1e-5 relative is therefore met with margin 0)."""
+import numpy as np
+import pytest
+import torch
+
+from parity_utils import (CudaAdapter, assert_bits_equal, assert_state_equal, gbm_ohlc, golden_traces, load_trace,
+                          oracle_state, replay_trace, stage_trace_series)
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5  # north-star tolerance for fp32 cash / position / reward / observation values
+
+
+def _env(series, **kw):
+    from finenvs_b200.environments import TimeSeriesEnv
+
+    return TimeSeriesEnv("golden", num_intervals=series.window, device_id=0, series=series, **kw)
+
+
+@pytest.mark.parametrize("name", golden_traces())
+@pytest.mark.parametrize("dtype,variant", [(torch.float32, "auto"), (torch.float64, "auto"), (torch.float32, "direct"),
+                                           (torch.float64, "direct")])
+def test_cuda_replays_reference_trace(name, dtype, variant):
+    z = load_trace(name)
+    series = stage_trace_series(z, dtype)
+    N = len(z["seg_init"])
+    env = _env(series, num_envs=N, evaluate=bool(z["evaluate"]), seed=int(z["seed"]), obs_dtype=dtype, variant=variant)
+    env._seg.copy_(torch.from_numpy(z["seg_init"]))
+    ad = CudaAdapter(env)
+    replay_trace(z, ad, ad.state, dtype == torch.float64, f"{name}[{variant}]")
+
+
+def _c1_series(W=60, days=1024, bars=252, sigma=0.01, seed=20260101):
+    from finenvs_b200.data import loader
+
+    rng = np.random.default_rng(seed)
+    prices = np.round(gbm_ohlc(rng, days * bars, sigma), 4)
+    seg_start, seg_len = loader.regular_segments(days * bars, bars, W)
+    return prices, seg_start, seg_len
+
+
+def _lockstep(env, ref, steps, rng, obs_every=1, action_fn=None):
+    ad = CudaAdapter(env)
+    assert_state_equal(oracle_state(ref), ad.state(), "init")
+    assert_bits_equal(ref.reset(), ad.reset(), "reset obs")
+    n_done = 0
+    for t in range(steps):
+        a = action_fn(rng, ref.N) if action_fn else rng.uniform(-1, 1, ref.N).astype(np.float32)
+        want = (t % obs_every) == 0
+        o_ref, r_ref, d_ref, i_ref = ref.step(a, want_obs=want)
+        o, r, d, info = ad.step(a)
+        assert_bits_equal(d_ref, d, f"dones t={t}")
+        assert_state_equal(oracle_state(ref), ad.state(), f"t={t}")
+        np.testing.assert_allclose(r, r_ref, rtol=RTOL, atol=0, err_msg=f"rewards t={t}")
+        assert_bits_equal(r_ref, r, f"rewards t={t}")
+        if want:
+            np.testing.assert_allclose(o, o_ref, rtol=RTOL, atol=0, err_msg=f"obs t={t}")
+            assert_bits_equal(o_ref, o, f"obs t={t}")
+        assert set(info) == set(i_ref)
+        n_done += int(d_ref.sum())
+    return n_done
+
+
+@pytest.mark.parametrize("mode,offset", [("last", False), ("all", True), ("keep", False)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_config1_1024_envs_vs_oracle(mode, offset, dtype):
+    """BASELINE config 1: single asset, GBM daily bars, 1024 envs, W=60, random actions; 2x252+ steps
+    so every env auto-resets at least twice."""
+    from oracle import oracle as orc
+    from finenvs_b200.data import loader
+
+    W = 60
+    prices, seg_start, seg_len = _c1_series(W)
+    series = loader.stage_series(prices, seg_start, seg_len, W, "cuda:0", dtype, keep_logret64=True)
+    assert series.num_segments == 1023
+    env = _env(series, seed=1234, random_reset=mode, random_offset=offset, obs_dtype=dtype)  # N = D + 1 = 1024
+    assert env.num_envs == 1024
+    fs = orc.series_from_prices(prices, seg_start, seg_len, W, logret=series.logret64.cpu().numpy())
+    ref = orc.OracleEnv(fs, num_envs=1024, seed=1234, reset_mode={"last": 1, "all": 2, "keep": 0}[mode],
+                        random_offset=offset, out_f64=dtype == torch.float64)
+    n_done = _lockstep(env, ref, 520, np.random.default_rng(1234), obs_every=7)
+    assert n_done >= 2 * 1024
+
+
+def test_adversarial_branches_vs_oracle():
+    """sigma=0.15 bars and short-biased actions: margin calls at High and Close, releases, bankruptcies,
+    blocked entries; ragged segment lengths; windows W=8 (tile) at N not a multiple of the tile."""
+    from oracle import oracle as orc
+    from finenvs_b200.data import loader
+
+    rng = np.random.default_rng(5)
+    bars = rng.integers(1, 60, 200)
+    W = 8
+    prices = np.round(gbm_ohlc(rng, int(bars.sum()) + W, 0.15), 4)
+    firsts = W + np.concatenate([[0], np.cumsum(bars)[:-1]])
+    seg_start, seg_len = firsts - W, (bars + W).astype(np.int32)
+    series = loader.stage_series(prices, seg_start, seg_len, W, "cuda:0", torch.float32, keep_logret64=True)
+    N = 5003
+    env = _env(series, num_envs=N, seed=9, random_reset="all", random_offset=True)
+    fs = orc.series_from_prices(prices, seg_start, seg_len, W, logret=series.logret64.cpu().numpy())
+    ref = orc.OracleEnv(fs, num_envs=N, seed=9, reset_mode=2, random_offset=True, out_f64=False)
+
+    def act(r, n):
+        a = r.uniform(-1, 1, n)
+        m = r.uniform(0, 1, n) < 0.6
+        a[m] = -np.abs(a[m])
+        return a.astype(np.float32)
+
+    n_done = _lockstep(env, ref, 300, rng, obs_every=3, action_fn=act)
+    assert n_done > 10000
+
+
+@pytest.mark.parametrize("W", [1, 3, 4, 61, 390, 1500, 2000])
+def test_window_sizes_and_variants(W):
+    """Odd windows (tail blocks whose byte count is not a multiple of 16), the reference default 390,
+    the largest windows the tile variant takes and one that must fall back to the direct variant."""
+    from oracle import oracle as orc
+    from finenvs_b200 import _lib
+    from finenvs_b200.data import loader
+
+    rng = np.random.default_rng(W)
+    bars, days = 20, 12
+    T = W + bars * days
+    prices = np.round(gbm_ohlc(rng, T, 0.02), 4)
+    firsts = W + bars * np.arange(days)
+    seg_start, seg_len = firsts - W, np.full(days, W + bars, np.int32)
+    for dtype in (torch.float32, torch.float64):
+        series = loader.stage_series(prices, seg_start, seg_len, W, "cuda:0", dtype, keep_logret64=True)
+        fs = orc.series_from_prices(prices, seg_start, seg_len, W, logret=series.logret64.cpu().numpy())
+        tile = _lib.lib().fe_tile_envs(W, int(dtype == torch.float64), 0)
+        for variant in (["auto", "direct"] if tile else ["auto"]):
+            N = 37
+            env = _env(series, num_envs=N, seed=3, random_reset="all", obs_dtype=dtype, variant=variant)
+            ref = orc.OracleEnv(fs, num_envs=N, seed=3, reset_mode=2, out_f64=dtype == torch.float64)
+            _lockstep(env, ref, 45, np.random.default_rng(W + 1))
+    if W == 2000:
+        assert _lib.lib().fe_tile_envs(W, 0, 0) == 0
+        series32 = loader.stage_series(prices, seg_start, seg_len, W, "cuda:0", torch.float32)
+        with pytest.raises(_lib.FeError):
+            _env(series32, num_envs=8, variant="tile").reset()
+
+
+def test_log_returns_kernel_vs_reference_values():
+    """fe_log_returns (:179-194) against the reference's own table (torch.log on CPU): <= 2 ulp."""
+    from finenvs_b200.data import loader
+
+    for name in ("trace_oih_w60.npz", "trace_spy_w390.npz", "trace_adv_s15_w8_n96.npz"):
+        z = load_trace(name)
+        s = loader.stage_series(z["prices"], z["seg_start"], z["seg_len_raw"], int(z["window"]), "cuda:0", torch.float32,
+                                keep_logret64=True)
+        got = s.logret64.cpu().numpy()
+        np.testing.assert_allclose(got, z["logret"], rtol=4e-16, atol=2e-14)
+        np.testing.assert_allclose(s.logret.cpu().numpy(), z["logret"].astype(np.float32), rtol=2e-7, atol=1e-12)
+        assert np.array_equal(s.seg_len.cpu().numpy(), s.seg_len_raw.cpu().numpy())
+
+
+def test_nan_rows_end_the_segment_like_the_reference_probe():
+    """A zero price makes log() NaN; the reference then treats the row as end-of-day padding (:486-496)."""
+    from oracle import oracle as orc
+    from finenvs_b200.data import loader
+
+    rng = np.random.default_rng(2)
+    W, bars, days = 4, 30, 6
+    prices = np.round(gbm_ohlc(rng, W + bars * days, 0.01), 4)
+    prices[W + 2 * bars + 10, 0] = -1.0   # log(neg/..) -> NaN in col 0 of that row ... and col 1-3 NaN too
+    firsts = W + bars * np.arange(days)
+    seg_start, seg_len = firsts - W, np.full(days, W + bars, np.int32)
+    series = loader.stage_series(prices, seg_start, seg_len, W, "cuda:0", torch.float64, keep_logret64=True)
+    fs = orc.series_from_prices(prices, seg_start, seg_len, W, logret=series.logret64.cpu().numpy())
+    assert np.array_equal(series.seg_len.cpu().numpy(), fs.seg_len)
+    assert fs.seg_len[2] == W + 10 and (fs.seg_len[[0, 1, 3, 4, 5]] == W + bars).all()
+    env = _env(series, num_envs=days, seed=1, random_reset="keep", obs_dtype=torch.float64)
+    ref = orc.OracleEnv(fs, num_envs=days, seed=1, reset_mode=0, out_f64=True)
+    _lockstep(env, ref, 70, rng)
+
+
+def test_evaluate_mode_returns_and_stats():
+    from oracle import oracle as orc
+    from finenvs_b200.data import loader
+
+    W = 16
+    prices, seg_start, seg_len = _c1_series(W, days=64, bars=40, sigma=0.03)
+    series = loader.stage_series(prices, seg_start, seg_len, W, "cuda:0", torch.float32, keep_logret64=True)
+    fs = orc.series_from_prices(prices, seg_start, seg_len, W, logret=series.logret64.cpu().numpy())
+    env = _env(series, evaluate=True, seed=2)
+    assert env.num_envs == series.num_segments
+    ref = orc.OracleEnv(fs, evaluate=True, seed=2, out_f64=False)
+    ad = CudaAdapter(env)
+    rng = np.random.default_rng(0)
+    n_info = 0
+    for t in range(130):
+        a = rng.uniform(-1, 1, ref.N).astype(np.float32)
+        o_ref, r_ref, d_ref, i_ref = ref.step(a)
+        o, r, d, info = ad.step(a)
+        assert_bits_equal(r_ref, r, f"rewards t={t}")
+        assert_bits_equal(d_ref, d, f"dones t={t}")
+        assert set(info) == set(i_ref)
+        if info:
+            n_info += 1
+            assert_bits_equal(i_ref["returns"], info["returns"], "returns")
+        assert_bits_equal(ref.ep_return, env.episode_returns.cpu().numpy(), f"ep_return t={t}")
+    assert n_info == 3
+
+
+def test_track_stats_matches_host_accounting():
+    from finenvs_b200.data import loader
+
+    W = 16
+    prices, seg_start, seg_len = _c1_series(W, days=64, bars=40, sigma=0.03)
+    series = loader.stage_series(prices, seg_start, seg_len, W, "cuda:0", torch.float32)
+    N = 3000
+    env = _env(series, num_envs=N, seed=2, random_reset="all", random_offset=True, track_stats=True)
+    g = torch.Generator().manual_seed(0)
+    ep_ret = np.zeros(N)
+    ep_len = np.zeros(N, np.int64)
+    fin_ret, fin_len = [], []
+    for t in range(100):
+        a = (torch.rand((N, 1), generator=g) * 2 - 1).cuda()
+        _, r, d, _ = env.step(a)
+        r, d = r.cpu().numpy().astype(np.float64), d.cpu().numpy().astype(bool)
+        ep_ret = (ep_ret + r).astype(np.float32).astype(np.float64)
+        ep_len += 1
+        fin_ret += list(ep_ret[d]); fin_len += list(ep_len[d])
+        ep_ret[d] = 0; ep_len[d] = 0
+    st = {k: v.item() for k, v in env.stats().items()}
+    assert st["n_done"] == len(fin_ret) > 0
+    assert st["sum_len"] == int(np.sum(fin_len))
+    np.testing.assert_allclose(st["sum_return"], np.sum(fin_ret), rtol=1e-9)
+    np.testing.assert_allclose(st["sum_return_sq"], np.sum(np.square(fin_ret)), rtol=1e-9)
+
+
+def test_sharding_does_not_change_results():
+    """Env-sharded run (two shards of one population, as two GPUs would hold) == unsharded run."""
+    from finenvs_b200.data import loader
+
+    W = 16
+    prices, seg_start, seg_len = _c1_series(W, days=64, bars=40, sigma=0.03)
+    series = loader.stage_series(prices, seg_start, seg_len, W, "cuda:0", torch.float32)
+    N, cut = 2048, 1100
+    kw = dict(seed=77, random_reset="all", random_offset=True)
+    full = _env(series, num_envs=N, **kw)
+    lo = _env(series, num_envs=cut, env_id_base=0, total_envs=N, **kw)
+    hi = _env(series, num_envs=N - cut, env_id_base=cut, total_envs=N, **kw)
+    g = torch.Generator().manual_seed(5)
+    for t in range(90):
+        a = (torch.rand((N, 1), generator=g) * 2 - 1).cuda()
+        o, r, d, _ = full.step(a)
+        o1, r1, d1, _ = lo.step(a[:cut].contiguous())
+        o2, r2, d2, _ = hi.step(a[cut:].contiguous())
+        assert torch.equal(o, torch.cat([o1, o2])) and torch.equal(r, torch.cat([r1, r2])) and torch.equal(d, torch.cat([d1, d2]))
+        assert torch.equal(full._seg, torch.cat([lo._seg, hi._seg])) and torch.equal(full._ptr, torch.cat([lo._ptr, hi._ptr]))
+    # reference-style "last env" redraw lives on the shard that owns the global last id
+    last_full = _env(series, num_envs=N, seed=3, random_reset="last")
+    last_hi = _env(series, num_envs=N - cut, env_id_base=cut, total_envs=N, seed=3, random_reset="last")
+    assert int(last_full._seg[-1]) == int(last_hi._seg[-1])
