@@ -228,8 +228,8 @@ def test_track_stats_matches_host_accounting():
     st = {k: v.item() for k, v in env.stats().items()}
     assert st["n_done"] == len(fin_ret) > 0
     assert st["sum_len"] == int(np.sum(fin_len))
-    np.testing.assert_allclose(st["sum_return"], np.sum(fin_ret), rtol=1e-9)
-    np.testing.assert_allclose(st["sum_return_sq"], np.sum(np.square(fin_ret)), rtol=1e-9)
+    np.testing.assert_allclose(st["sum_return"], np.sum(fin_ret), rtol=1e-6)  # host side re-rounds the f32 rewards
+    np.testing.assert_allclose(st["sum_return_sq"], np.sum(np.square(fin_ret)), rtol=1e-6)
 
 
 def test_sharding_does_not_change_results():
