@@ -21,13 +21,13 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace {
 
 constexpr int kThreads = 128;          // threads per block (both variants)
 constexpr int kMaxTileEnvs = kThreads; // one bookkeeping thread per env of the tile
 constexpr int kSmemHeader = 16;        // mbarrier (8 B) + pad
-constexpr int kSmemTarget = 72 * 1024; // aim for 3 resident blocks per SM
 constexpr int kSmemMax = 226 * 1024;
 
 // ------------------------------------------------------------------------------------------
@@ -376,7 +376,7 @@ fe_tile_kernel(const FeParams p, const FeSeries s, const FeState st, const Const
     const int nrows = nvalid * W;
     const float invW = 1.0f / (float)W;
     const Row4<OutT> *in_rows = reinterpret_cast<const Row4<OutT> *>(in_tile);
-    for (int row = tid; row < nrows; row += kThreads) {
+    for (int row = tid; row < nrows; row += blockDim.x) {
         const int e = __float2int_rz(((float)row + 0.5f) * invW);
         const Row4<OutT> v = in_rows[row];
         OutT *o = out_tile + (size_t)row * 5;
@@ -400,7 +400,7 @@ fe_tile_kernel(const FeParams p, const FeSeries s, const FeState st, const Const
         }
     } else { // ragged tail block whose byte count is not a multiple of 16
         __syncthreads();
-        for (int f = tid; f < nrows * 5; f += kThreads) dst[f] = out_tile[f];
+        for (int f = tid; f < nrows * 5; f += blockDim.x) dst[f] = out_tile[f];
     }
 }
 
@@ -520,24 +520,47 @@ int check_common(const FeParams *p, const FeSeries *s, const FeState *st) {
     return 0;
 }
 
-int pick_tile_envs(int W, bool f64) {
+// Tile shape.  Measured on B200 (tools/sweep_tile.sh, 1 Mi envs, W=60): the step is latency-bound per
+// block (state loads -> table lookup -> window copy -> interleave -> store), so MANY SMALL blocks in
+// flight beat few large ones: 4 envs x 32 threads (23 blocks/SM) runs 0.35 ms where 32 envs x 128
+// threads (3 blocks/SM) runs 0.46 ms.  E is kept a multiple of 4 so that every full tile's byte count
+// (E*W*20) is a multiple of 16 for any W (bulk-copy granularity).
+int pick_tile_envs(int W, bool f64, int *threads_out = nullptr) {
     const size_t sz = f64 ? 8 : 4;
-    auto fit = [&](size_t budget) {
-        long e = (long)((budget - kSmemHeader - 16) / ((size_t)W * 9 * sz + sz));
-        if (e > kMaxTileEnvs) e = kMaxTileEnvs;
-        return (int)(e & ~3L); // multiple of 4 keeps every full tile's byte count a multiple of 16
-    };
-    int e = fit(kSmemTarget);
-    if (e < 8) e = fit(kSmemMax);
-    return e < 4 ? 0 : e;
+    const size_t per_env = (size_t)W * 9 * sz + sz;
+    long e_max = (long)((kSmemMax - kSmemHeader - 16) / per_env) & ~3L;
+    if (e_max < 4) return 0;
+    long e = 4;
+    while (e * W < 192 && e < kMaxTileEnvs) e += 4; // tiny windows: keep >= ~200 rows per block
+    if (e > e_max) e = e_max;
+    long rows = e * W;
+    int threads = (int)(((rows / 8) + 31) & ~31L);
+    if (threads < 32) threads = 32;
+    if (threads > kThreads) threads = kThreads;
+    while (threads < e) threads += 32;
+    if (threads_out) *threads_out = threads;
+    return (int)e;
+}
+
+// tuning overrides (sweeps only): FE_TILE_ENVS (multiple of 4), FE_TILE_THREADS (multiple of 32, <= 128)
+int env_override(const char *name) {
+    const char *v = getenv(name);
+    return v ? atoi(v) : 0;
 }
 
 template <typename OutT, bool kObserve>
 int launch(const FeParams &p, const FeSeries &s, const FeState &st, const float *actions, void *obs, void *rewards,
            int32_t *dones, FeStats *stats, uint64_t step, cudaStream_t stream) {
     const Consts k = make_consts(p);
-    int E = p.variant == FE_VARIANT_DIRECT ? 0 : pick_tile_envs(p.window, sizeof(OutT) == 8);
+    int threads = kThreads;
+    int E = p.variant == FE_VARIANT_DIRECT ? 0 : pick_tile_envs(p.window, sizeof(OutT) == 8, &threads);
     if (p.variant == FE_VARIANT_TILE && E == 0) return FE_ESMEM;
+    if (E > 0) {
+        static const int ov_e = env_override("FE_TILE_ENVS"), ov_t = env_override("FE_TILE_THREADS");
+        if (ov_e >= 4 && tile_smem_bytes<OutT>(ov_e & ~3, p.window) <= (size_t)kSmemMax) E = ov_e & ~3;
+        if (ov_t >= 32 && ov_t <= kThreads) threads = ov_t & ~31;
+        if (E > threads) E = threads;
+    }
     if (E > 0) {
         if ((uintptr_t)obs & 15) return FE_EALIGN;
         const size_t smem = tile_smem_bytes<OutT>(E, p.window);
@@ -550,7 +573,7 @@ int launch(const FeParams &p, const FeSeries &s, const FeState &st, const float 
             configured[dev] = kSmemMax;
         }
         const int64_t blocks = (p.num_envs + E - 1) / E;
-        kern<<<(unsigned)blocks, kThreads, smem, stream>>>(p, s, st, k, actions, (OutT *)obs, (OutT *)rewards, dones,
+        kern<<<(unsigned)blocks, threads, smem, stream>>>(p, s, st, k, actions, (OutT *)obs, (OutT *)rewards, dones,
                                                            stats, step, E);
     } else {
         const int64_t blocks = (p.num_envs + kThreads - 1) / kThreads;

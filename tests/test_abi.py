@@ -69,11 +69,14 @@ def test_host_philox_matches_oracle_and_known_answer(built):
 
 def test_tile_sizes(built):
     L = built.lib()
-    assert L.fe_tile_envs(60, 0, 0) == 32      # 32 envs x 60 rows x 36 B = 69 KB -> 3 blocks / SM
-    assert L.fe_tile_envs(60, 1, 0) == 16
-    assert L.fe_tile_envs(390, 0, 0) == 16     # the reference default window
-    assert L.fe_tile_envs(128, 0, 0) % 4 == 0
-    assert L.fe_tile_envs(2000, 0, 0) == 0     # falls back to the direct variant
+    # small tiles (many blocks in flight) measured fastest; always a multiple of 4 (16-byte bulk-copy granularity)
+    assert L.fe_tile_envs(60, 0, 0) == 4 and L.fe_tile_envs(60, 1, 0) == 4
+    assert L.fe_tile_envs(390, 0, 0) == 4      # the reference default window
+    assert L.fe_tile_envs(4, 0, 0) == 48       # tiny windows: more envs per block
+    for w in (1, 3, 8, 16, 128, 1500):
+        assert L.fe_tile_envs(w, 0, 0) % 4 == 0 and L.fe_tile_envs(w, 0, 0) > 0
+    assert L.fe_tile_envs(1500, 1, 0) == 0     # f64 rows: does not fit -> direct variant
+    assert L.fe_tile_envs(2000, 0, 0) == 0
     assert L.fe_tile_envs(0, 0, 0) == 0
 
 
