@@ -60,14 +60,21 @@ def make_series(workload: str, W: int):
     rng = np.random.default_rng(SERIES_SEED)
     if workload == "c4":     # minute bars, 10 M rows, 390-bar segments
         T, bars, sigma = 10_000_000, 390, 0.0005
-    else:                    # c2 / c1: daily bars, 1024 segments x 252 bars
+    else:                    # c2 / c1 / c3: daily bars, 1024 segments x 252 bars
         T, bars, sigma = 1024 * 252, 252, 0.01
-    prices = np.round(gbm_ohlc(rng, T, sigma), 4)
+    if workload == "c3":     # 30 independent GBM assets, time-major (T, A, 4)
+        prices = np.stack([np.round(gbm_ohlc(rng, T, sigma, s0=20.0 + 7 * a), 4) for a in range(WORKLOAD_ASSETS["c3"])], axis=1)
+    else:
+        prices = np.round(gbm_ohlc(rng, T, sigma), 4)
     seg_start, seg_len = loader.regular_segments(T, bars, W)
     return prices, seg_start, seg_len, {"rows": T, "bars_per_segment": bars, "sigma": sigma}
 
 
+WORKLOAD_ASSETS = {"c2": 1, "c4": 1, "c3": 30}
+WORKLOAD_DEFAULTS = {"c2": (1 << 20, 60), "c4": (1 << 20, 60), "c3": (65536, 128)}   # (envs per GPU, window)
+
 WORKLOAD_NAMES = {
+    "c3": "30-asset portfolio-allocation env, 65536 envs, 128-step window, transaction costs, 1 B200",
     "c2": "single-asset env, 1M envs, 60-step window, fused step kernel on 1 B200 vs reference",
     "c4": "synthetic minute-bar series of 10M timesteps, 1M envs per GPU with random start offsets, env-sharded",
 }
@@ -143,16 +150,18 @@ def cpu_oracle_throughput(W: int, workload: str, sample_envs: int, steps: int, w
                         out_f64=False)
     threads = orc.lib().feo_num_threads()
     rng = np.random.default_rng(ACTION_SEED)
-    acts = [rng.uniform(-1, 1, sample_envs).astype(np.float32) for _ in range(4)]
-    obs = np.empty((sample_envs, W, 5), np.float32)
+    A = WORKLOAD_ASSETS[workload]
+    acts = [rng.uniform(-1, 1, sample_envs * A).astype(np.float32) for _ in range(4)]
+    obs = np.empty((sample_envs, W, 5 * A), np.float32)
     rewards = np.empty(sample_envs, np.float32)
     dones = np.empty(sample_envs, np.int32)
     import ctypes as C
 
     def one(i):
         env.step_count += 1
-        orc.lib().feo_step(C.byref(env.p), C.byref(env.s), C.byref(env.st), orc._p(acts[i % 4]), orc._p(obs),
-                           orc._p(rewards), orc._p(dones), env.step_count, None)
+        fn = orc.lib().feo_step_multi if env.multi else orc.lib().feo_step
+        fn(C.byref(env.p), C.byref(env.s), C.byref(env.st), orc._p(acts[i % 4]), orc._p(obs),
+           orc._p(rewards), orc._p(dones), env.step_count, None)
 
     for i in range(warmup):
         one(i)
@@ -171,7 +180,7 @@ def run_reference_arm(args, rank: int):
     """--impl reference: the reference's algorithm on the box's host cores (oracle port, all threads)."""
     if rank != 0:
         return
-    sample = min(args.envs, 262144)
+    sample = min(args.envs, 262144 // WORKLOAD_ASSETS[args.workload] // (2 if args.workload == "c3" else 1))
     v, sps, threads, n = cpu_oracle_throughput(args.window, args.workload, sample, args.steps, args.warmup, None)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
@@ -188,9 +197,9 @@ def run_reference_arm(args, rank: int):
 
 def workload_config(args, world: int):
     return {"workload": WORKLOAD_NAMES[args.workload], "envs_per_gpu": args.envs, "total_envs": args.envs * world,
-            "window": args.window, "assets": 1, "obs_dtype": "float32", "reset": "all envs redraw (segment, offset), Philox",
+            "window": args.window, "assets": WORKLOAD_ASSETS[args.workload], "obs_dtype": "float32", "reset": "all envs redraw (segment, offset), Philox",
             "parallelism": f"env-sharded x{world}, series replicated, no per-step collective",
-            "l2": "per-step working set (obs 1.2 GB + state) >> 126 MB L2: no flush needed"}
+            "l2": "per-step working set (obs >= 1.2 GB + state) >> 126 MB L2: no flush needed"}
 
 
 # ------------------------------------------------------------------------------ GPU arm ------
@@ -200,13 +209,16 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4"])
-    ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
-    ap.add_argument("--window", type=int, default=60)
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"])
+    ap.add_argument("--envs", type=int, default=None, help="envs per GPU (default: 1 Mi; c3: 65536)")
+    ap.add_argument("--window", type=int, default=None, help="default 60; c3: 128")
     ap.add_argument("--variant", default="auto", choices=["auto", "tile", "direct"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    args.envs = args.envs or WORKLOAD_DEFAULTS[args.workload][0]
+    args.window = args.window or WORKLOAD_DEFAULTS[args.workload][1]
+    A = WORKLOAD_ASSETS[args.workload]
 
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":
@@ -233,8 +245,8 @@ def main():
 
     # inputs resident in HBM: a ring of pre-generated action batches
     g = torch.Generator(device=dev).manual_seed(ACTION_SEED + rank)
-    ring = [torch.rand((N, 1), generator=g, device=dev) * 2 - 1 for _ in range(8)]
-    obs = torch.empty((N, W, 5), dtype=torch.float32, device=dev)
+    ring = [torch.rand((N, A), generator=g, device=dev) * 2 - 1 for _ in range(8)]
+    obs = torch.empty((N, W, 5 * A), dtype=torch.float32, device=dev)
     rewards = torch.empty(N, dtype=torch.float32, device=dev)
     dones = torch.empty(N, dtype=torch.int32, device=dev)
     ring_host = [a.cpu().pin_memory() for a in ring[:4]]
@@ -284,7 +296,7 @@ def main():
 
     value = total * args.steps / (dev_ms * 1e-3)
     e2e_value = total * args.steps / (e2e_ms * 1e-3)
-    bytes_per_launch = algorithmic_bytes_per_env_step(W) * N
+    bytes_per_launch = algorithmic_bytes_per_env_step(W, A) * N
     kernel_s = dev_ms * 1e-3 / args.steps   # only fe_step launches sit between the two events
     achieved = bytes_per_launch / kernel_s / 1e9
     peak, peak_src = 6650.0, "fallback"
@@ -312,18 +324,20 @@ def main():
         "dtype": "f32/f64", "data": "synthetic", "config": {**workload_config(args, world), **meta},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": f"of {peak_src}",
-                     "algorithmic_bytes_per_env_step": algorithmic_bytes_per_env_step(W), "kernel": "fe_tile_kernel<float,false>",
+                     "algorithmic_bytes_per_env_step": algorithmic_bytes_per_env_step(W, A),
+                     "kernel": "fe_portfolio_kernel<float,false>" if A > 1 else "fe_tile_kernel<float,false>",
                      "kernel_ms": kernel_s * 1e3},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * N, "d2h_bytes_per_step": 8 * N,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * N * A, "d2h_bytes_per_step": 8 * N,
                 "ms_per_step": e2e_ms / args.steps, "api": "TimeSeriesEnv.step_host -> fe_step_host (pinned host buffers)"},
         "gpu_launches": 2 * args.steps,   # fe_step kernels inside the two timed regions (device + e2e)
         "clocks": sampler.summary(),
         "episodes_finished_last_step": n_done,
     }
     if world == 1 and not args.no_cpu_baseline:
-        v, sps, threads, n = cpu_oracle_throughput(W, args.workload, min(N, 262144), 10_000, 3, 12.0)
+        sample = min(N, 262144 // A // (2 if A > 1 else 1))
+        v, sps, threads, n = cpu_oracle_throughput(W, args.workload, sample, 10_000, 3, 12.0)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"{min(N, 262144)} envs per step, {n} steps (~12 s), oracle/fe_oracle.c, OpenMP {threads} threads"}
+                                "sample": f"{sample} envs per step, {n} steps (~12 s), oracle/fe_oracle.c, OpenMP {threads} threads"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

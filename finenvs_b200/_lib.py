@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfinenvs_b200.so")
 
 RESET_KEEP, RESET_LAST, RESET_ALL = 0, 1, 2
-VARIANT_AUTO, VARIANT_TILE, VARIANT_DIRECT = 0, 1, 2
+VARIANT_AUTO, VARIANT_TILE, VARIANT_DIRECT, VARIANT_PORTFOLIO = 0, 1, 2, 3
 ABI_VERSION = 1
 
 

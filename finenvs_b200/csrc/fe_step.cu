@@ -445,6 +445,282 @@ fe_direct_kernel(const FeParams p, const FeSeries s, const FeState st, const Con
 }
 
 // ------------------------------------------------------------------------------------------
+// portfolio variant (A > 1 assets, one cash account): EXTENSION, the reference is single-asset (:223).
+// Semantics: the reference's phases in the reference's order; inside a phase the
+// assets are visited in index order, each applying the A = 1 arithmetic to (cash, asset a).  One block
+// per env; warp 0 does the bookkeeping with lane = asset: every per-asset quantity is lane-local, only
+// the f32 cash chain is serial, walked with warp shuffles (all lanes keep an identical copy of cash).
+// Per-env sums (reward, share count) are xor-butterfly warp reductions.  The whole block then streams
+// the (W, A, 4) window in chunks: bulk copy in -> interleave 4->5 -> bulk store, double buffered.
+// ------------------------------------------------------------------------------------------
+constexpr int kPortThreads = 128;
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+__device__ __forceinline__ double warp_sum64(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = dadd(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum32(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fadd(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+
+// executed by all 32 lanes of warp 0; lane >= A is a neutral asset (no shares, no action, price 1).
+// Per-asset deltas are exchanged through three 32-double scratch rows in shared memory (broadcast LDS, whose
+// addresses do not depend on the cash chain, so the loads run ahead of it); the serial part is only
+// cvt -> DADD -> cvt per asset.  (A first version walked the chain with __shfl_sync inside the loops:
+// ncu showed ~10 k instructions per env in this warp, WARPSYNC.COLLECTIVE wrappers around every shuffle.)
+template <typename OutT>
+__device__ __forceinline__ void portfolio_step(const FeParams &p, const FeSeries &s, const FeState &st, const Consts &k,
+                                               const int64_t i, const int32_t seg_in, const int32_t ptr_in,
+                                               const int64_t row0, const float *__restrict__ actions,
+                                               OutT *__restrict__ rewards, int32_t *__restrict__ dones, FeStats *stats,
+                                               const uint64_t step, OutT *pf_smem, double *scratch) {
+    const int A = p.num_assets, W = p.window;
+    const int lane = threadIdx.x & 31;
+    const bool act = lane < A;
+    const int64_t ia = i * A + lane;
+    double *xa = scratch, *xb = scratch + 32, *xc = scratch + 64; // __syncwarp() orders the exchanges
+    double O = 1.0, H = 1.0, L = 1.0, C = 1.0, margin = 0.0;
+    float lng = 0.0f, sht = 0.0f, d = 0.0f;
+    if (act) {
+        const double2 *px = reinterpret_cast<const double2 *>(s.prices + ((row0 + W - 1) * A + lane) * 4);
+        const double2 oh = __ldg(px), lc = __ldg(px + 1);
+        O = oh.x; H = oh.y; L = lc.x; C = lc.y;
+        lng = st.long_sh[ia]; sht = st.short_sh[ia]; margin = st.margin[ia];
+        d = rintf(fmul(__ldg(actions + ia), k.scale));                       // :298-302
+        d = d < -k.ms ? -k.ms : (d > k.ms ? k.ms : d);
+    }
+    float cash = st.cash[i];
+    const int32_t len = __ldg(s.seg_len + seg_in);
+    float comm = 0.0f;
+    float pos = d < 0.0f ? 0.0f : d, neg = d > 0.0f ? 0.0f : d;             // :344-351
+    const double Omc = dsub(O, k.c), Opc = dadd(O, k.c);
+    { // :353-361 sell longs ; :367-383 cover shorts, re-mark margin (all three deltas are cash-independent)
+        const float nl = relu32(fadd(lng, neg));
+        const float sold = fsub(lng, nl);
+        neg = fadd(neg, sold);
+        comm = fadd(comm, fmul(sold, k.cf));
+        lng = nl;
+        xa[lane] = dmul((double)sold, Omc);
+        const float ns = relu32(fsub(sht, pos));
+        const float bought = fsub(sht, ns);
+        pos = fsub(pos, bought);
+        comm = fadd(comm, fmul(bought, k.cf));
+        sht = ns;
+        xb[lane] = dmul((double)bought, Opc);
+        const double nm = dmul((double)fmul(k.imrf, sht), O);
+        xc[lane] = dsub(nm, margin);
+        margin = nm;
+        __syncwarp();
+        for (int a = 0; a < A; ++a) cash = d2f(dadd((double)cash, xa[a]));
+        for (int a = 0; a < A; ++a) {
+            cash = d2f(dsub((double)cash, xb[a]));
+            cash = d2f(dsub((double)cash, xc[a]));
+        }
+        __syncwarp();
+    }
+    { // :385-399 long entries, greedy in asset order
+        xa[lane] = dmul((double)pos, Opc);
+        __syncwarp();
+        unsigned blocked_mask = 0;
+        for (int a = 0; a < A; ++a) {
+            const double ca = xa[a];
+            const bool blocked = dsub((double)cash, ca) < 0.0;
+            if (!blocked) cash = d2f(dsub((double)cash, ca));
+            blocked_mask |= (blocked ? 1u : 0u) << a;
+        }
+        if ((blocked_mask >> lane) & 1u) pos = 0.0f;
+        comm = fadd(comm, fmul(pos, k.cf));
+        lng = fadd(lng, pos);
+        __syncwarp();
+    }
+    { // :401-421 short entries, greedy in asset order
+        float q = -neg;
+        float sc = fmul(q, k.cf);
+        double req = dmul(k.imr, dmul((double)q, O));
+        xa[lane] = req;
+        xb[lane] = (double)sc;
+        __syncwarp();
+        unsigned blocked_mask = 0;
+        for (int a = 0; a < A; ++a) {
+            const double ra = xa[a], sa = xb[a];
+            const bool blocked = dsub(dsub((double)cash, ra), sa) < 0.0;
+            if (!blocked) cash = d2f(dsub((double)cash, dadd(ra, sa)));
+            blocked_mask |= (blocked ? 1u : 0u) << a;
+        }
+        if ((blocked_mask >> lane) & 1u) { q = -0.0f; sc = fmul(q, k.cf); req = dmul(k.imr, dmul((double)q, O)); }
+        comm = fadd(comm, fmul(q, k.cf));
+        margin = dadd(margin, req);
+        sht = fadd(sht, q);
+        __syncwarp();
+    }
+    // :428-431 position feature, built before rewards / dones / reset
+    if (act) pf_smem[lane] = (OutT)__ddiv_rn(dmul((double)fsub(lng, sht), C), k.SB);
+    int done = cash < 0.0f;                                                  // :448
+    const double mc1 = relu64(dsub(dmul(dmul((double)sht, H), k.mmr1), margin)); // :459-468 at High
+    margin = dadd(margin, mc1);
+    const double rel = relu64(dsub(margin, dmul(dmul((double)sht, L), k.imr)));  // :470-475 at Low
+    margin = dsub(margin, rel);
+    const double mc2 = relu64(dsub(dmul(dmul((double)sht, C), k.mmr1), margin)); // :451 at Close
+    margin = dadd(margin, mc2);
+    xa[lane] = mc1; xb[lane] = rel; xc[lane] = mc2;
+    __syncwarp();
+    for (int a = 0; a < A; ++a) {
+        cash = d2f(dsub((double)cash, xa[a]));
+        done |= cash < 0.0f;
+    }
+    for (int a = 0; a < A; ++a) cash = d2f(dadd((double)cash, xb[a]));
+    for (int a = 0; a < A; ++a) {
+        cash = d2f(dsub((double)cash, xc[a]));
+        done |= cash < 0.0f;
+    }
+    double r = dadd(-mc1, -mc2);
+    if (done) { lng = 0.0f; sht = 0.0f; }                                    // :452-453
+    r = dadd(r, dmul((double)fsub(lng, sht), dsub(C, O)));                   // :454-455
+    r = dsub(r, (double)comm);                                               // :456
+    double rew = warp_sum64(act ? r : 0.0);
+    const float nsh = warp_sum32(act ? fadd(sht, lng) : 0.0f);               // :288
+    int32_t seg = seg_in, ptr = ptr_in;
+    done |= (ptr + W >= len);                                                // :477-496
+    rew = dsub(rew, (double)fmul(fmul(done ? 1.0f : 0.0f, nsh), k.cf));      // :288-289
+    if (done) {                                                              // :498-521
+        cash = k.SBf; margin = 0.0; lng = 0.0f; sht = 0.0f; ptr = 0;
+        const int64_t gid = p.env_id_base + i;
+        if (p.reset_mode == FE_RESET_ALL || (p.reset_mode == FE_RESET_LAST && gid == p.total_envs - 1))
+            draw_segment(p, s, gid, step, 0u, seg, ptr);
+    }
+    if (act) { st.long_sh[ia] = lng; st.short_sh[ia] = sht; st.margin[ia] = margin; }
+    if (lane == 0) {
+        if (p.evaluate) {                                                    // :523-536
+            const int was = st.terminated[i];
+            if (was) rew = 0.0;
+            if (done && !was) { st.terminated[i] = 1; if (stats) atomicAdd(&stats->n_terminated, 1ULL); }
+            st.ep_return[i] = d2f(dadd((double)st.ep_return[i], rew));
+            if (done && stats) atomicAdd(&stats->n_done, 1ULL);
+        } else if (stats) {
+            const float er = d2f(dadd((double)st.ep_return[i], rew));
+            const int32_t el = st.ep_len[i] + 1;
+            if (done) {
+                atomicAdd(&stats->n_done, 1ULL);
+                atomicAdd(&stats->sum_len, (unsigned long long)el);
+                atomicAdd(&stats->sum_return, (double)er);
+                atomicAdd(&stats->sum_return_sq, (double)er * (double)er);
+            }
+            st.ep_return[i] = done ? 0.0f : er;
+            st.ep_len[i] = done ? 0 : el;
+        }
+        st.seg[i] = seg; st.ptr[i] = ptr; st.cash[i] = cash;
+        rewards[i] = (OutT)rew;
+        dones[i] = done;
+    }
+}
+
+// smem: [2 mbarriers 16 B][pf 32 x OutT -> 256 B][scratch 3 x 32 doubles][in[2]: CH*4 OutT each][out[2]: CH*5 OutT each]
+constexpr int kPortHeader = 16 + 256 + 768;
+template <typename OutT> __host__ __device__ inline size_t port_smem_bytes(int CH) {
+    return kPortHeader + (size_t)2 * CH * 9 * sizeof(OutT);
+}
+
+template <typename OutT, bool kObserve>
+__global__ void __launch_bounds__(kPortThreads)
+fe_portfolio_kernel(const FeParams p, const FeSeries s, const FeState st, const Consts k,
+                    const float *__restrict__ actions, OutT *__restrict__ obs, OutT *__restrict__ rewards,
+                    int32_t *__restrict__ dones, FeStats *stats, const uint64_t step, const int CH) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int W = p.window, A = p.num_assets;
+    const int tid = threadIdx.x;
+    const int64_t i = blockIdx.x;
+    const int P = W * A;                         // (row, asset) pairs of one env's window
+    const int nchunks = (P + CH - 1) / CH;
+    OutT *pf = reinterpret_cast<OutT *>(smem + 16);
+    double *scratch = reinterpret_cast<double *>(smem + 16 + 256);
+    unsigned char *in0 = smem + kPortHeader;
+    const size_t in_bytes = (size_t)CH * 4 * sizeof(OutT), out_bytes = (size_t)CH * 5 * sizeof(OutT);
+    unsigned char *out0 = in0 + 2 * in_bytes;
+    const uint32_t bar0 = smem_u32(smem);
+    // every thread reads the pointer BEFORE warp 0 may overwrite it at the end of its bookkeeping
+    const int32_t seg = st.seg[i];
+    const int32_t ptr = st.ptr[i] + (kObserve ? 0 : 1);
+    const int64_t row0 = __ldg(s.seg_start + seg) + ptr;
+    const unsigned char *src = reinterpret_cast<const unsigned char *>(s.logret) + (size_t)row0 * A * 4 * sizeof(OutT);
+    OutT *dst = obs + (size_t)i * P * 5;
+    const bool bulk_out = (P & 3) == 0;          // then every chunk of every env is 16-byte aligned and sized
+    if (tid == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto load_chunk = [&](int c) { // thread 0 only
+        const int n = min(CH, P - c * CH);
+        const uint32_t bytes = (uint32_t)n * 4 * sizeof(OutT);
+        const uint32_t bar = bar0 + 8 * (c & 1);
+        mbar_arrive_expect_tx(bar, bytes);
+        bulk_load(smem_u32(in0 + (c & 1) * in_bytes), src + (size_t)c * in_bytes, bytes, bar);
+    };
+    if (tid == 0) {
+        load_chunk(0);
+        if (nchunks > 1) load_chunk(1);
+    }
+    if (tid < 32) {
+        if (kObserve) {
+            if (tid < A) {
+                const double C = __ldg(s.prices + ((row0 + W - 1) * A + tid) * 4 + 3);
+                const float net = fsub(st.long_sh[i * A + tid], st.short_sh[i * A + tid]);
+                pf[tid] = (OutT)__ddiv_rn(dmul((double)net, C), k.SB);
+            }
+        } else {
+            portfolio_step<OutT>(p, s, st, k, i, seg, ptr, row0, actions, rewards, dones, stats, step, pf, scratch);
+        }
+    }
+    __syncthreads(); // pf visible
+    const float invA = 1.0f / (float)A;
+    for (int c = 0; c < nchunks; ++c) {
+        const int sidx = c & 1;
+        const int n = min(CH, P - c * CH);
+        mbar_wait(bar0 + 8 * sidx, (c >> 1) & 1);
+        if (c >= 2) { // out[sidx] is being read by the store of chunk c-2: allow only chunk c-1's store in flight
+            if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncthreads();
+        }
+        const Row4<OutT> *in_rows = reinterpret_cast<const Row4<OutT> *>(in0 + sidx * in_bytes);
+        OutT *out_tile = reinterpret_cast<OutT *>(out0 + sidx * out_bytes);
+        const int g0 = c * CH;
+        for (int r = tid; r < n; r += kPortThreads) {
+            const int g = g0 + r;
+            const int a = g - __float2int_rz(((float)g + 0.5f) * invA) * A;
+            const Row4<OutT> v = in_rows[r];
+            OutT *o = out_tile + (size_t)r * 5;
+            if constexpr (sizeof(OutT) == 4) {
+                o[0] = v.v.x; o[1] = v.v.y; o[2] = v.v.z; o[3] = v.v.w;
+            } else {
+                o[0] = v.a.x; o[1] = v.a.y; o[2] = v.b.x; o[3] = v.b.y;
+            }
+            o[4] = pf[a];
+        }
+        OutT *d = dst + (size_t)g0 * 5;
+        if (bulk_out) {
+            fence_proxy_async_smem();
+            __syncthreads(); // out tile complete, in tile fully consumed
+            if (tid == 0) {
+                bulk_store(d, smem_u32(out_tile), (uint32_t)((size_t)n * 5 * sizeof(OutT)));
+                bulk_commit();
+                if (c + 2 < nchunks) load_chunk(c + 2);
+            }
+        } else {
+            __syncthreads();
+            for (int f = tid; f < n * 5; f += kPortThreads) d[f] = out_tile[f];
+            __syncthreads();
+            if (tid == 0 && c + 2 < nchunks) load_chunk(c + 2);
+        }
+    }
+    if (tid == 0) bulk_wait_read_all();
+}
+
+// ------------------------------------------------------------------------------------------
 // reset_all, log-returns, effective segment length
 // ------------------------------------------------------------------------------------------
 __global__ void fe_reset_all_kernel(const FeParams p, const FeSeries s, const FeState st, const uint64_t step,
@@ -452,9 +728,11 @@ __global__ void fe_reset_all_kernel(const FeParams p, const FeSeries s, const Fe
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.num_envs) return;
     st.cash[i] = (float)p.starting_balance;
-    st.margin[i] = 0.0;
-    st.long_sh[i] = 0.0f;
-    st.short_sh[i] = 0.0f;
+    for (int a = 0; a < p.num_assets; ++a) {
+        st.margin[i * p.num_assets + a] = 0.0;
+        st.long_sh[i * p.num_assets + a] = 0.0f;
+        st.short_sh[i * p.num_assets + a] = 0.0f;
+    }
     int32_t ptr = 0;
     if (redraw) {
         int32_t seg;
@@ -512,7 +790,7 @@ __global__ void fe_effective_len_kernel(const double *__restrict__ lr64, const i
 int check_common(const FeParams *p, const FeSeries *s, const FeState *st) {
     if (!p || !s || !st) return FE_EINVAL;
     if (p->num_envs <= 0 || p->window <= 0 || p->num_segments <= 0 || p->num_rows <= 0) return FE_EINVAL;
-    if (p->num_assets != 1) return FE_EINVAL;
+    if (p->num_assets < 1 || p->num_assets > 32) return FE_EINVAL;
     if (!s->prices || !s->logret || !s->seg_start || !s->seg_len) return FE_EINVAL;
     if (!st->seg || !st->ptr || !st->cash || !st->long_sh || !st->short_sh || !st->margin) return FE_EINVAL;
     if (p->evaluate && (!st->terminated || !st->ep_return)) return FE_EINVAL;
@@ -552,6 +830,26 @@ template <typename OutT, bool kObserve>
 int launch(const FeParams &p, const FeSeries &s, const FeState &st, const float *actions, void *obs, void *rewards,
            int32_t *dones, FeStats *stats, uint64_t step, cudaStream_t stream) {
     const Consts k = make_consts(p);
+    if (p.num_assets > 1 || p.variant == FE_VARIANT_PORTFOLIO) {
+        if ((uintptr_t)obs & 15) return FE_EALIGN;
+        const int P = p.window * p.num_assets;
+        int CH = 256; // pairs per chunk (4 KB in + 5 KB out, x2 stages): measured best of 128..1024 on C3 (1.73 ms)
+        static const int ov_ch = env_override("FE_PORT_CHUNK");
+        if (ov_ch >= 4) CH = ov_ch & ~3;
+        if (CH > ((P + 3) & ~3)) CH = (P + 3) & ~3;
+        const size_t smem = port_smem_bytes<OutT>(CH);
+        if (smem > (size_t)kSmemMax) return FE_ESMEM;
+        auto kern = fe_portfolio_kernel<OutT, kObserve>;
+        static bool configured[16] = {false};
+        if (!configured[p.device & 15]) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+            if (e != cudaSuccess) return (int)e;
+            configured[p.device & 15] = true;
+        }
+        kern<<<(unsigned)p.num_envs, kPortThreads, smem, stream>>>(p, s, st, k, actions, (OutT *)obs, (OutT *)rewards,
+                                                                  dones, stats, step, CH);
+        return (int)cudaGetLastError();
+    }
     int threads = kThreads;
     int E = p.variant == FE_VARIANT_DIRECT ? 0 : pick_tile_envs(p.window, sizeof(OutT) == 8, &threads);
     if (p.variant == FE_VARIANT_TILE && E == 0) return FE_ESMEM;
@@ -603,7 +901,7 @@ int fe_version(void) { return FE_ABI_VERSION; }
 const char *fe_error_string(int code) {
     switch (code) {
     case 0: return "ok";
-    case FE_EINVAL: return "finenvs_b200: invalid argument (null pointer, non-positive size or num_assets != 1)";
+    case FE_EINVAL: return "finenvs_b200: invalid argument (null pointer, non-positive size or num_assets outside 1..32)";
     case FE_EALIGN: return "finenvs_b200: pointer not 16-byte aligned";
     case FE_ESMEM: return "finenvs_b200: window too large for the tile variant";
     default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "finenvs_b200: unknown error";

@@ -116,8 +116,8 @@ def regular_segments(num_rows: int, bars_per_segment: int, window: int):
 class StagedSeries:
     """The series resident in HBM (device tensors) + the small host-side facts about it."""
 
-    prices: torch.Tensor      # (T, 4) f64
-    logret: torch.Tensor      # (T, 4) f32 or f64 (matches the observation dtype)
+    prices: torch.Tensor      # (T, 4) f64, or (T, A, 4) time-major for an A-asset portfolio
+    logret: torch.Tensor      # same shape, f32 or f64 (matches the observation dtype)
     seg_start: torch.Tensor   # (D,) i64
     seg_len: torch.Tensor     # (D,) i32 effective
     seg_len_raw: torch.Tensor  # (D,) i32
@@ -131,6 +131,10 @@ class StagedSeries:
     @property
     def num_segments(self) -> int:
         return int(self.seg_start.shape[0])
+
+    @property
+    def num_assets(self) -> int:
+        return 1 if self.prices.dim() == 2 else int(self.prices.shape[1])
 
     @property
     def device(self) -> torch.device:
@@ -149,9 +153,12 @@ def stage_series(prices, seg_start, seg_len_raw, window: int, device: str, obs_d
     if dev.type != "cuda":
         raise RuntimeError("stage_series needs a CUDA device (no CPU path)")
     prices_h = torch.as_tensor(np.ascontiguousarray(prices, dtype=np.float64)) if not torch.is_tensor(prices) else prices
-    if prices_h.dim() != 2 or prices_h.shape[1] != 4:
-        raise ValueError(f"prices must be (T, 4) O,H,L,C; got {tuple(prices_h.shape)}")
+    if prices_h.dim() not in (2, 3) or prices_h.shape[-1] != 4:
+        raise ValueError(f"prices must be (T, 4) or (T, A, 4) O,H,L,C; got {tuple(prices_h.shape)}")
     T = int(prices_h.shape[0])
+    A = 1 if prices_h.dim() == 2 else int(prices_h.shape[1])
+    if not 1 <= A <= 32:
+        raise ValueError("1 <= num_assets <= 32")
     seg_start_h = torch.as_tensor(np.ascontiguousarray(seg_start, dtype=np.int64))
     raw_h = torch.as_tensor(np.ascontiguousarray(seg_len_raw, dtype=np.int32))
     if seg_start_h.numel() == 0:
@@ -168,13 +175,13 @@ def stage_series(prices, seg_start, seg_len_raw, window: int, device: str, obs_d
         seg_start_d = seg_start_h.to(dev)
         raw_d = raw_h.to(dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        lr64 = torch.empty((T, 4), dtype=torch.float64, device=dev)
+        lr64 = torch.empty(prices_d.shape, dtype=torch.float64, device=dev)
         want32 = obs_dtype == torch.float32
-        lr32 = torch.empty((T, 4), dtype=torch.float32, device=dev) if want32 else None
-        _lib.check(L.fe_log_returns(prices_d.data_ptr(), T, 1, lr64.data_ptr(), lr32.data_ptr() if want32 else None,
+        lr32 = torch.empty(prices_d.shape, dtype=torch.float32, device=dev) if want32 else None
+        _lib.check(L.fe_log_returns(prices_d.data_ptr(), T, A, lr64.data_ptr(), lr32.data_ptr() if want32 else None,
                                     stream), "fe_log_returns")
         seg_len_d = torch.empty_like(raw_d)
-        _lib.check(L.fe_effective_len(lr64.data_ptr(), seg_start_d.data_ptr(), raw_d.data_ptr(), raw_d.numel(), window, 1,
+        _lib.check(L.fe_effective_len(lr64.data_ptr(), seg_start_d.data_ptr(), raw_d.data_ptr(), raw_d.numel(), window, A,
                                       seg_len_d.data_ptr(), stream), "fe_effective_len")
         torch.cuda.current_stream(dev).synchronize()
     logret = lr32 if want32 else lr64

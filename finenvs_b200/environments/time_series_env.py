@@ -34,7 +34,8 @@ except Exception:  # pragma: no cover - gym is not installed in the target image
         Box = _Box
 
 _RESET_MODES = {"keep": _lib.RESET_KEEP, "last": _lib.RESET_LAST, "all": _lib.RESET_ALL}
-_VARIANTS = {"auto": _lib.VARIANT_AUTO, "tile": _lib.VARIANT_TILE, "direct": _lib.VARIANT_DIRECT}
+_VARIANTS = {"auto": _lib.VARIANT_AUTO, "tile": _lib.VARIANT_TILE, "direct": _lib.VARIANT_DIRECT,
+             "portfolio": _lib.VARIANT_PORTFOLIO}
 
 
 class TimeSeriesEnv(BaseObject):
@@ -108,6 +109,7 @@ class TimeSeriesEnv(BaseObject):
             if series.logret.dtype != obs_dtype:
                 raise ValueError(f"series log-returns are {series.logret.dtype}, obs_dtype is {obs_dtype}")
         self.series = series
+        self.num_assets = series.num_assets   # extension: A > 1 = portfolio env sharing one cash account
         self.values_per_interval = 4
         self.set_spaces()
         if random_reset is None:
@@ -122,8 +124,8 @@ class TimeSeriesEnv(BaseObject):
 
     # ------------------------------------------------------------------ metadata (:218-243) ----
     def set_spaces(self) -> None:
-        self.num_obs = self.values_per_interval + 1
-        self.num_acts = 1
+        self.num_obs = (self.values_per_interval + 1) * self.num_assets
+        self.num_acts = self.num_assets
         self.action_space = _spaces.Box(np.ones(self.num_acts) * -1.0, np.ones(self.num_acts) * +1.0, dtype=np.float64)
         self.observation_space = _spaces.Box(
             np.ones((self.num_intervals, self.num_obs)) * -np.inf,
@@ -158,9 +160,10 @@ class TimeSeriesEnv(BaseObject):
         self._seg = (gid % D).to(torch.int32)
         self._ptr = torch.zeros(N, dtype=torch.int32, device=dev)
         self._cash = torch.full((N,), float(self.starting_balance), dtype=torch.float32, device=dev)
-        self._long = torch.zeros(N, dtype=torch.float32, device=dev)
-        self._short = torch.zeros(N, dtype=torch.float32, device=dev)
-        self._margin = torch.zeros(N, dtype=torch.float64, device=dev)
+        A = self.num_assets
+        self._long = torch.zeros(N * A, dtype=torch.float32, device=dev)
+        self._short = torch.zeros(N * A, dtype=torch.float32, device=dev)
+        self._margin = torch.zeros(N * A, dtype=torch.float64, device=dev)
         need_ep = self.evaluate or self.track_stats
         self._terminated = torch.zeros(N, dtype=torch.uint8, device=dev) if self.evaluate else None
         self._ep_return = torch.zeros(N, dtype=torch.float32, device=dev) if need_ep else None
@@ -168,7 +171,7 @@ class TimeSeriesEnv(BaseObject):
         self._stats = torch.zeros(_lib.STATS_BYTES // 8, dtype=torch.int64, device=dev) if need_ep else None
         self.step_count = 0
         self._params = _lib.FeParams(
-            N, base, total, self.series.num_rows, self.num_intervals, D, 1, int(self.max_shares),
+            N, base, total, self.series.num_rows, self.num_intervals, D, A, int(self.max_shares),
             float(self.starting_balance), float(self.per_share_commission), float(self.initial_margin_requirement),
             float(self.maintenance_margin_requirement), self.seed, _RESET_MODES[self.random_reset],
             int(self.random_offset), int(self.evaluate), int(self.obs_dtype == torch.float64), variant,
@@ -218,15 +221,15 @@ class TimeSeriesEnv(BaseObject):
 
     @property
     def long_shares(self) -> torch.Tensor:
-        return self._long.view(-1, 1)
+        return self._long.view(self.num_envs, self.num_assets)
 
     @property
     def short_shares(self) -> torch.Tensor:
-        return self._short.view(-1, 1)
+        return self._short.view(self.num_envs, self.num_assets)
 
     @property
     def margin(self) -> torch.Tensor:
-        return self._margin.view(-1, 1)
+        return self._margin.view(self.num_envs, self.num_assets)
 
     @property
     def terminated_episodes(self) -> torch.Tensor:
@@ -253,8 +256,9 @@ class TimeSeriesEnv(BaseObject):
     def _prepare_actions(self, actions: torch.Tensor) -> torch.Tensor:
         if not torch.is_tensor(actions):
             raise TypeError("actions must be a torch.Tensor")
-        if actions.numel() != self.num_envs:
-            raise ValueError(f"actions must have {self.num_envs} elements (num_envs, 1); got {tuple(actions.shape)}")
+        if actions.numel() != self.num_envs * self.num_acts:
+            raise ValueError(f"actions must be (num_envs, num_acts) = ({self.num_envs}, {self.num_acts}); "
+                             f"got {tuple(actions.shape)}")
         if actions.device != self._dev or actions.dtype != torch.float32 or not actions.is_contiguous():
             actions = actions.to(device=self._dev, dtype=torch.float32, non_blocking=True).contiguous()
         return actions
@@ -286,11 +290,11 @@ class TimeSeriesEnv(BaseObject):
         the observation stays in HBM.  Per step: 4N bytes host->device, 8N (f32) device->host."""
         if actions_host.device.type != "cpu" or actions_host.dtype != torch.float32 or not actions_host.is_contiguous():
             raise ValueError("actions_host must be a contiguous float32 CPU tensor")
-        if actions_host.numel() != self.num_envs:
-            raise ValueError(f"actions must have {self.num_envs} elements")
+        if actions_host.numel() != self.num_envs * self.num_acts:
+            raise ValueError(f"actions must have {self.num_envs * self.num_acts} elements")
         if not hasattr(self, "_host_bufs"):
             self._host_bufs = (
-                torch.empty(self.num_envs, dtype=torch.float32, device=self._dev),
+                torch.empty(self.num_envs * self.num_acts, dtype=torch.float32, device=self._dev),
                 torch.empty(self.num_envs, dtype=self.obs_dtype, device=self._dev),
                 torch.empty(self.num_envs, dtype=torch.int32, device=self._dev),
                 torch.empty(self.num_envs, dtype=self.obs_dtype).pin_memory(),

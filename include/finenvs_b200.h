@@ -40,6 +40,7 @@ extern "C" {
 #define FE_VARIANT_AUTO 0   /* bulk-copy (TMA) tile kernel when the window fits in shared memory, else direct */
 #define FE_VARIANT_TILE 1   /* cp.async.bulk in -> smem interleave -> cp.async.bulk out */
 #define FE_VARIANT_DIRECT 2 /* warp-per-env global->global copy (any window) */
+#define FE_VARIANT_PORTFOLIO 3 /* block-per-env, lane-per-asset kernel; always used when num_assets > 1 */
 
 typedef struct FeParams {
     int64_t num_envs;        /* envs held by this GPU (a shard) */
@@ -48,7 +49,7 @@ typedef struct FeParams {
     int64_t num_rows;        /* T: rows of the flat series */
     int32_t window;          /* W = num_intervals (:19) */
     int32_t num_segments;    /* D: trading days / segments */
-    int32_t num_assets;      /* A: 1 for the reference env */
+    int32_t num_assets;      /* A: 1 for the reference env; 2..32 = portfolio extension (series (T,A,4), obs (N,W,A,5)) */
     int32_t max_shares;      /* :20 */
     double starting_balance; /* :21 */
     double commission;       /* per_share_commission :22 */
@@ -65,7 +66,7 @@ typedef struct FeParams {
 
 /* Series staged once into HBM (replaces the two NaN-padded (D,L,4) tensors of :196-216). */
 typedef struct FeSeries {
-    const double *prices;     /* (T, A, 4) f64 O,H,L,C            (:169-177) */
+    const double *prices;     /* (T, A, 4) f64 O,H,L,C, time-major  (:169-177) */
     const void *logret;       /* (T, A, 4) 100*log-returns, float when !out_f64 else double (:179-194) */
     const int64_t *seg_start; /* (D,) first row of segment d: first bar of the day minus W history rows (:141-152) */
     const int32_t *seg_len;   /* (D,) rows in segment d with the NaN probe of :486-496 folded in */

@@ -276,6 +276,206 @@ int64_t feo_step(const FeoParams *p, const FeoSeries *s, const FeoState *st, con
     return n_done;
 }
 
+/* ------------------------------------------------------------------ multi-asset (A > 1) -----
+ * EXTENSION with no reference implementation (the reference is single-asset, :223); SURVEY App. D.
+ * Definition: shared f32 cash, per-asset long/short/margin; the reference's phases run in the
+ * reference's order and INSIDE each phase the assets are visited in index order, each applying the
+ * reference's A = 1 arithmetic to (cash, asset a) — so legality is evaluated against the cash left by
+ * the assets before it (greedy prefix order), and A = 1 reduces to feo_step() exactly (tested on every
+ * golden trace).  Per-env sums over assets (reward, share count) use the xor-butterfly order of a warp
+ * reduction so that the CUDA kernel can reproduce them bit for bit. */
+#define FEO_MAX_ASSETS 32
+
+static double butterfly_sum64(const double *v, int A) {
+    double w[32];
+    for (int i = 0; i < 32; ++i) w[i] = i < A ? v[i] : 0.0;
+    for (int off = 16; off > 0; off >>= 1) {
+        double n[32];
+        for (int i = 0; i < 32; ++i) n[i] = w[i] + w[i ^ off];
+        memcpy(w, n, sizeof(w));
+    }
+    return w[0];
+}
+
+static float butterfly_sum32(const float *v, int A) {
+    float w[32];
+    for (int i = 0; i < 32; ++i) w[i] = i < A ? v[i] : 0.0f;
+    for (int off = 16; off > 0; off >>= 1) {
+        float n[32];
+        for (int i = 0; i < 32; ++i) n[i] = w[i] + w[i ^ off];
+        memcpy(w, n, sizeof(w));
+    }
+    return w[0];
+}
+
+/* obs (N, W, A, 5): row j, asset a = [logret[row0+j, a, 0..3], posfeat_a] */
+static void write_obs_multi(const FeoParams *p, const FeoSeries *s, void *obs, int64_t i, int64_t row0,
+                            const double *posfeat) {
+    const int W = p->window, A = p->num_assets;
+    for (int j = 0; j < W; ++j)
+        for (int a = 0; a < A; ++a) {
+            const size_t src = ((size_t)(row0 + j) * A + a) * 4;
+            const size_t dst = (((size_t)i * W + j) * A + a) * 5;
+            if (p->out_f64) {
+                double *o = (double *)obs + dst;
+                for (int c = 0; c < 4; ++c) o[c] = s->logret[src + c];
+                o[4] = posfeat[a];
+            } else {
+                float *o = (float *)obs + dst;
+                for (int c = 0; c < 4; ++c) o[c] = s->logret32[src + c];
+                o[4] = (float)posfeat[a];
+            }
+        }
+}
+
+void feo_observe_multi(const FeoParams *p, const FeoSeries *s, const FeoState *st, void *obs) {
+    const int W = p->window, A = p->num_assets;
+#pragma omp parallel for schedule(static) if (p->num_envs >= 1024)
+    for (int64_t i = 0; i < p->num_envs; ++i) {
+        const int64_t row0 = s->seg_start[st->seg[i]] + st->ptr[i];
+        double pf[FEO_MAX_ASSETS];
+        for (int a = 0; a < A; ++a) {
+            const double C = s->prices[((size_t)(row0 + W - 1) * A + a) * 4 + 3];
+            const float net = st->long_sh[i * A + a] - st->short_sh[i * A + a];
+            pf[a] = ((double)net * C) / p->starting_balance;
+        }
+        write_obs_multi(p, s, obs, i, row0, pf);
+    }
+}
+
+int64_t feo_step_multi(const FeoParams *p, const FeoSeries *s, const FeoState *st, const float *actions,
+                       void *obs, void *rewards, int32_t *dones, uint64_t step_counter,
+                       int32_t *all_terminated) {
+    const int W = p->window, A = p->num_assets;
+    const float ms = (float)p->max_shares;
+    const float scale = (float)((double)p->max_shares + 0.5);
+    const double c = p->commission;
+    const float cf = (float)p->commission;
+    const float imrf = (float)p->imr;
+    const double imr = p->imr;
+    const double mmr1 = 1.0 + p->mmr;
+    const double SB = p->starting_balance;
+    const float SBf = (float)p->starting_balance;
+    int64_t n_done = 0, n_not_terminated = 0;
+
+#pragma omp parallel for schedule(static) reduction(+ : n_done, n_not_terminated) if (p->num_envs >= 1024)
+    for (int64_t i = 0; i < p->num_envs; ++i) {
+        float pos[FEO_MAX_ASSETS], neg[FEO_MAX_ASSETS], lng[FEO_MAX_ASSETS], sht[FEO_MAX_ASSETS], comm[FEO_MAX_ASSETS];
+        double margin[FEO_MAX_ASSETS], O[FEO_MAX_ASSETS], H[FEO_MAX_ASSETS], L[FEO_MAX_ASSETS], C[FEO_MAX_ASSETS];
+        double mc1[FEO_MAX_ASSETS], mc2[FEO_MAX_ASSETS], r[FEO_MAX_ASSETS], pf[FEO_MAX_ASSETS];
+        int32_t seg = st->seg[i];
+        int32_t ptr = st->ptr[i] + 1;
+        const int64_t row0 = s->seg_start[seg] + ptr;
+        float cash = st->cash[i];
+        for (int a = 0; a < A; ++a) {
+            float d = rintf(actions[i * A + a] * scale);                 /* :298-302 */
+            d = d < -ms ? -ms : (d > ms ? ms : d);
+            pos[a] = d < 0.0f ? 0.0f : d;                                /* :344-351 */
+            neg[a] = d > 0.0f ? 0.0f : d;
+            const double *px = s->prices + ((size_t)(row0 + W - 1) * A + a) * 4;
+            O[a] = px[0]; H[a] = px[1]; L[a] = px[2]; C[a] = px[3];
+            lng[a] = st->long_sh[i * A + a]; sht[a] = st->short_sh[i * A + a]; margin[a] = st->margin[i * A + a];
+            comm[a] = 0.0f;
+        }
+        for (int a = 0; a < A; ++a) {                                    /* :353-361 */
+            const float nl = relu32(lng[a] + neg[a]);
+            const float sold = lng[a] - nl;
+            neg[a] = neg[a] + sold;
+            comm[a] = comm[a] + sold * cf;
+            cash = (float)((double)cash + (double)sold * (O[a] - c));
+            lng[a] = nl;
+        }
+        for (int a = 0; a < A; ++a) {                                    /* :367-383 */
+            const float ns = relu32(sht[a] - pos[a]);
+            const float bought = sht[a] - ns;
+            pos[a] = pos[a] - bought;
+            comm[a] = comm[a] + bought * cf;
+            cash = (float)((double)cash - (double)bought * (O[a] + c));
+            sht[a] = ns;
+            const double nm = (double)(imrf * sht[a]) * O[a];
+            cash = (float)((double)cash - (nm - margin[a]));
+            margin[a] = nm;
+        }
+        for (int a = 0; a < A; ++a) {                                    /* :385-399 */
+            if (((double)cash - (double)pos[a] * (O[a] + c)) < 0.0) pos[a] = 0.0f;
+            comm[a] = comm[a] + pos[a] * cf;
+            cash = (float)((double)cash - (double)pos[a] * (O[a] + c));
+            lng[a] = lng[a] + pos[a];
+        }
+        for (int a = 0; a < A; ++a) {                                    /* :401-421 */
+            float q = -neg[a];
+            float sc = q * cf;
+            double req = imr * ((double)q * O[a]);
+            if ((((double)cash - req) - (double)sc) < 0.0) {
+                q = -0.0f;
+                sc = q * cf;
+                req = imr * ((double)q * O[a]);
+            }
+            comm[a] = comm[a] + q * cf;
+            cash = (float)((double)cash - (req + (double)sc));
+            margin[a] = margin[a] + req;
+            sht[a] = sht[a] + q;
+        }
+        for (int a = 0; a < A; ++a) pf[a] = ((double)(lng[a] - sht[a]) * C[a]) / SB;   /* :428-431 */
+        if (obs) write_obs_multi(p, s, obs, i, row0, pf);
+        int done = cash < 0.0f;                                          /* :448 */
+        for (int a = 0; a < A; ++a) {                                    /* :459-468 at High */
+            mc1[a] = relu64(((double)sht[a] * H[a]) * mmr1 - margin[a]);
+            cash = (float)((double)cash - mc1[a]);
+            margin[a] = margin[a] + mc1[a];
+            done |= cash < 0.0f;
+        }
+        for (int a = 0; a < A; ++a) {                                    /* :470-475 at Low */
+            const double rel = relu64(margin[a] - ((double)sht[a] * L[a]) * imr);
+            margin[a] = margin[a] - rel;
+            cash = (float)((double)cash + rel);
+        }
+        for (int a = 0; a < A; ++a) {                                    /* :451 at Close */
+            mc2[a] = relu64(((double)sht[a] * C[a]) * mmr1 - margin[a]);
+            cash = (float)((double)cash - mc2[a]);
+            margin[a] = margin[a] + mc2[a];
+            done |= cash < 0.0f;
+        }
+        float held[FEO_MAX_ASSETS];
+        for (int a = 0; a < A; ++a) {
+            double ra = (-mc1[a]) + (-mc2[a]);
+            if (done) { lng[a] = 0.0f; sht[a] = 0.0f; }                  /* :452-453 */
+            ra = ra + (double)(lng[a] - sht[a]) * (C[a] - O[a]);         /* :454-455 */
+            r[a] = ra - (double)comm[a];                                 /* :456 */
+            held[a] = sht[a] + lng[a];                                   /* :288 */
+        }
+        double rew = butterfly_sum64(r, A);
+        const float nsh = butterfly_sum32(held, A);
+        done |= (ptr + W >= s->seg_len[seg]);                            /* :477-496 */
+        rew = rew - (double)(((done ? 1.0f : 0.0f) * nsh) * cf);         /* :288-289 */
+        if (done) {                                                      /* :498-521 */
+            cash = SBf; ptr = 0;
+            for (int a = 0; a < A; ++a) { margin[a] = 0.0; lng[a] = 0.0f; sht[a] = 0.0f; }
+            const int64_t gid = p->env_id_base + i;
+            if (p->reset_mode == FEO_RESET_ALL || (p->reset_mode == FEO_RESET_LAST && gid == p->total_envs - 1)) {
+                int32_t nseg, off;
+                feo_draw(p, s, gid, step_counter, 0u, &nseg, &off);
+                seg = nseg; ptr = off;
+            }
+            ++n_done;
+        }
+        if (p->evaluate) {                                               /* :523-536 */
+            if (st->terminated[i]) rew = 0.0;
+            if (done) st->terminated[i] = 1;
+            st->ep_return[i] = (float)((double)st->ep_return[i] + rew);
+            if (!st->terminated[i]) ++n_not_terminated;
+        }
+        st->seg[i] = seg; st->ptr[i] = ptr; st->cash[i] = cash;
+        for (int a = 0; a < A; ++a) {
+            st->long_sh[i * A + a] = lng[a]; st->short_sh[i * A + a] = sht[a]; st->margin[i * A + a] = margin[a];
+        }
+        if (p->out_f64) ((double *)rewards)[i] = rew; else ((float *)rewards)[i] = (float)rew;
+        dones[i] = done;
+    }
+    if (all_terminated) *all_terminated = p->evaluate && n_not_terminated == 0;
+    return n_done;
+}
+
 /* Extension: start a fresh episode everywhere; optional redraw of (segment, offset).
  * Mirrors the state :245-269 allocates. */
 void feo_reset_all(const FeoParams *p, const FeoSeries *s, const FeoState *st, uint64_t step_counter,
@@ -283,7 +483,12 @@ void feo_reset_all(const FeoParams *p, const FeoSeries *s, const FeoState *st, u
     const float SBf = (float)p->starting_balance;
 #pragma omp parallel for schedule(static) if (p->num_envs >= 4096)
     for (int64_t i = 0; i < p->num_envs; ++i) {
-        st->cash[i] = SBf; st->margin[i] = 0.0; st->long_sh[i] = 0.0f; st->short_sh[i] = 0.0f;
+        st->cash[i] = SBf;
+        for (int a = 0; a < p->num_assets; ++a) {
+            st->margin[i * p->num_assets + a] = 0.0;
+            st->long_sh[i * p->num_assets + a] = 0.0f;
+            st->short_sh[i * p->num_assets + a] = 0.0f;
+        }
         st->ptr[i] = 0;
         if (redraw) {
             int32_t seg, off;

@@ -89,6 +89,12 @@ void feo_observe(const FeoParams *p, const FeoSeries *s, const FeoState *st, voi
 int64_t feo_step(const FeoParams *p, const FeoSeries *s, const FeoState *st, const float *actions,
                  void *obs, void *rewards, int32_t *dones, uint64_t step_counter, int32_t *all_terminated);
 
+/* EXTENSION without a reference implementation: A > 1 assets sharing one cash account (A <= 32);
+ * series are time-major (T, A, 4), obs is (N, W, A, 5).  At A = 1 identical to feo_step/feo_observe. */
+void feo_observe_multi(const FeoParams *p, const FeoSeries *s, const FeoState *st, void *obs);
+int64_t feo_step_multi(const FeoParams *p, const FeoSeries *s, const FeoState *st, const float *actions,
+                       void *obs, void *rewards, int32_t *dones, uint64_t step_counter, int32_t *all_terminated);
+
 /* extension: fresh episode for every env (mirrors isaac_gym_env.py:55-58 reset_all). */
 void feo_reset_all(const FeoParams *p, const FeoSeries *s, const FeoState *st, uint64_t step_counter,
                    int32_t redraw);

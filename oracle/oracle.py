@@ -106,6 +106,10 @@ def lib():
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
                                C.POINTER(C.c_int32)]
         L.feo_step.restype = C.c_int64
+        L.feo_observe_multi.argtypes = L.feo_observe.argtypes
+        L.feo_observe_multi.restype = None
+        L.feo_step_multi.argtypes = L.feo_step.argtypes
+        L.feo_step_multi.restype = C.c_int64
         L.feo_reset_all.argtypes = [C.POINTER(FeoParams), C.POINTER(FeoSeries), C.POINTER(FeoState),
                                     C.c_uint64, C.c_int32]
         L.feo_reset_all.restype = None
@@ -130,9 +134,9 @@ def philox(seed: int, env_id: int, step: int, kind: int = 0) -> np.ndarray:
 class FlatSeries:
     """Flat series + segment table (the HBM layout, on the host)."""
 
-    prices: np.ndarray      # (T, 4) f64 OHLC
-    logret: np.ndarray      # (T, 4) f64
-    logret32: np.ndarray    # (T, 4) f32
+    prices: np.ndarray      # (T, 4) f64 OHLC, or (T, A, 4) time-major for A assets
+    logret: np.ndarray      # same shape, f64
+    logret32: np.ndarray    # same shape, f32
     seg_start: np.ndarray   # (D,) i64
     seg_len_raw: np.ndarray  # (D,) i32 = W + bars of the day
     seg_len: np.ndarray     # (D,) i32 effective (NaN probe folded in)
@@ -141,6 +145,10 @@ class FlatSeries:
     @property
     def num_segments(self) -> int:
         return int(self.seg_start.shape[0])
+
+    @property
+    def num_assets(self) -> int:
+        return 1 if self.prices.ndim == 2 else int(self.prices.shape[1])
 
     @property
     def max_len(self) -> int:
@@ -162,17 +170,18 @@ def series_from_prices(prices: np.ndarray, seg_start: np.ndarray, seg_len_raw: n
                        logret: np.ndarray | None = None) -> FlatSeries:
     prices = np.ascontiguousarray(prices, dtype=np.float64)
     T = prices.shape[0]
+    A = 1 if prices.ndim == 2 else prices.shape[1]
     if logret is None:
-        logret = np.empty((T, 4), dtype=np.float64)
-        lr32 = np.empty((T, 4), dtype=np.float32)
-        lib().feo_log_returns(_p(prices), T, 1, _p(logret), _p(lr32))
+        logret = np.empty(prices.shape, dtype=np.float64)
+        lr32 = np.empty(prices.shape, dtype=np.float32)
+        lib().feo_log_returns(_p(prices), T, A, _p(logret), _p(lr32))
     else:
         logret = np.ascontiguousarray(logret, dtype=np.float64)
         lr32 = logret.astype(np.float32)
     seg_start = np.ascontiguousarray(seg_start, dtype=np.int64)
     seg_len_raw = np.ascontiguousarray(seg_len_raw, dtype=np.int32)
     eff = np.array(
-        [lib().feo_effective_len(_p(logret), int(s), int(n), window, 1) for s, n in zip(seg_start, seg_len_raw)],
+        [lib().feo_effective_len(_p(logret), int(s), int(n), window, A) for s, n in zip(seg_start, seg_len_raw)],
         dtype=np.int32,
     )
     return FlatSeries(prices, logret, lr32, seg_start, seg_len_raw, eff, window)
@@ -205,13 +214,17 @@ def load_csv(path: str, window: int) -> FlatSeries:
 
 # ------------------------------------------------------------------------------- env -------
 class OracleEnv:
-    """Host-side env with the same semantics the CUDA path implements (A = 1)."""
+    """Host-side env with the same semantics the CUDA path implements.  A = 1 runs the restatement of
+    the reference (feo_step); A > 1 (or force_multi) runs the multi-asset extension (feo_step_multi)."""
 
     def __init__(self, series: FlatSeries, num_envs: int | None = None, *, max_shares=5,
                  starting_balance=10000.0, commission=0.01, imr=1.5, mmr=0.25, evaluate=False,
                  seed=0, reset_mode: int | None = None, random_offset=False, out_f64=True,
-                 env_id_base=0, total_envs: int | None = None, seg_init: np.ndarray | None = None):
+                 env_id_base=0, total_envs: int | None = None, seg_init: np.ndarray | None = None,
+                 force_multi: bool = False):
         self.series = series
+        self.A = A = series.num_assets
+        self.multi = force_multi or A > 1
         D = series.num_segments
         if reset_mode is None:
             reset_mode = RESET_KEEP if evaluate else RESET_LAST
@@ -220,7 +233,7 @@ class OracleEnv:
         if total_envs is None:
             total_envs = num_envs
         self.N = N = int(num_envs)
-        self.p = FeoParams(N, env_id_base, total_envs, series.prices.shape[0], series.window, D, 1,
+        self.p = FeoParams(N, env_id_base, total_envs, series.prices.shape[0], series.window, D, A,
                            max_shares, starting_balance, commission, imr, mmr, seed, reset_mode,
                            int(random_offset), int(evaluate), int(out_f64))
         self._keep = [series.prices, series.logret, series.logret32, series.seg_start, series.seg_len]
@@ -228,9 +241,10 @@ class OracleEnv:
         self.seg = np.zeros(N, np.int32)
         self.ptr = np.zeros(N, np.int32)
         self.cash = np.full(N, starting_balance, np.float32)
-        self.long_sh = np.zeros(N, np.float32)
-        self.short_sh = np.zeros(N, np.float32)
-        self.margin = np.zeros(N, np.float64)
+        shp = N if A == 1 else (N, A)
+        self.long_sh = np.zeros(shp, np.float32)
+        self.short_sh = np.zeros(shp, np.float32)
+        self.margin = np.zeros(shp, np.float64)
         self.terminated = np.zeros(N, np.uint8)
         self.ep_return = np.zeros(N, np.float32)
         self.st = FeoState(_p(self.seg), _p(self.ptr), _p(self.cash), _p(self.long_sh), _p(self.short_sh),
@@ -254,8 +268,9 @@ class OracleEnv:
         return seg.value, off.value
 
     def reset(self) -> np.ndarray:
-        obs = np.empty((self.N, self.series.window, 5), self.obs_dtype)
-        lib().feo_observe(C.byref(self.p), C.byref(self.s), C.byref(self.st), _p(obs))
+        obs = np.empty((self.N, self.series.window, 5 * self.A), self.obs_dtype)
+        fn = lib().feo_observe_multi if self.multi else lib().feo_observe
+        fn(C.byref(self.p), C.byref(self.s), C.byref(self.st), _p(obs))
         return obs
 
     def reset_all(self, redraw: bool | None = None) -> np.ndarray:
@@ -265,14 +280,15 @@ class OracleEnv:
         return self.reset()
 
     def step(self, actions: np.ndarray, want_obs: bool = True):
-        actions = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.N)
-        obs = np.empty((self.N, self.series.window, 5), self.obs_dtype) if want_obs else None
+        actions = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.N * self.A)
+        obs = np.empty((self.N, self.series.window, 5 * self.A), self.obs_dtype) if want_obs else None
         rewards = np.empty(self.N, self.obs_dtype)
         dones = np.empty(self.N, np.int32)
         allt = C.c_int32(0)
         self.step_count += 1
-        lib().feo_step(C.byref(self.p), C.byref(self.s), C.byref(self.st), _p(actions), _p(obs), _p(rewards),
-                       _p(dones), self.step_count, C.byref(allt))
+        fn = lib().feo_step_multi if self.multi else lib().feo_step
+        fn(C.byref(self.p), C.byref(self.s), C.byref(self.st), _p(actions), _p(obs), _p(rewards),
+           _p(dones), self.step_count, C.byref(allt))
         info = {}
         if self.p.evaluate and allt.value:           # :531-534
             info = {"returns": self.ep_return.copy()}

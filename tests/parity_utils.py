@@ -125,7 +125,7 @@ class CudaAdapter:
     def step(self, actions):
         import torch
 
-        a = torch.from_numpy(np.ascontiguousarray(actions, dtype=np.float32)).view(-1, 1).to(self.env.device)
+        a = torch.from_numpy(np.ascontiguousarray(actions, dtype=np.float32)).view(self.env.num_envs, -1).to(self.env.device)
         o, r, d, info = self.env.step(a)
         return o.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy(), {k: v.cpu().numpy() for k, v in info.items()}
 

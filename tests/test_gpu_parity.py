@@ -22,7 +22,8 @@ def _env(series, **kw):
 
 @pytest.mark.parametrize("name", golden_traces())
 @pytest.mark.parametrize("dtype,variant", [(torch.float32, "auto"), (torch.float64, "auto"), (torch.float32, "direct"),
-                                           (torch.float64, "direct")])
+                                           (torch.float64, "direct"), (torch.float32, "portfolio"),
+                                           (torch.float64, "portfolio")])
 def test_cuda_replays_reference_trace(name, dtype, variant):
     z = load_trace(name)
     series = stage_trace_series(z, dtype)
@@ -256,3 +257,60 @@ def test_sharding_does_not_change_results():
     last_full = _env(series, num_envs=N, seed=3, random_reset="last")
     last_hi = _env(series, num_envs=N - cut, env_id_base=cut, total_envs=N, seed=3, random_reset="last")
     assert int(last_full._seg[-1]) == int(last_hi._seg[-1])
+
+
+# ------------------------------------------------------------------ portfolio (A > 1) extension ----
+def _portfolio_series(A, W, days, bars, sigma, seed):
+    from finenvs_b200.data import loader
+
+    rng = np.random.default_rng(seed)
+    T = days * bars
+    prices = np.stack([np.round(gbm_ohlc(rng, T, sigma, s0=20.0 + 7 * a), 4) for a in range(A)], axis=1)  # (T, A, 4)
+    seg_start, seg_len = loader.regular_segments(T, bars, W)
+    return prices, seg_start, seg_len
+
+
+@pytest.mark.parametrize("A,W,N,sigma,dtype", [(30, 128, 384, 0.01, torch.float32), (30, 128, 96, 0.01, torch.float64),
+                                               (5, 7, 1001, 0.1, torch.float32), (3, 5, 257, 0.12, torch.float64),
+                                               (32, 16, 200, 0.05, torch.float32), (2, 60, 333, 0.08, torch.float32)])
+def test_portfolio_env_vs_oracle(A, W, N, sigma, dtype):
+    """BASELINE config 3 shape (30 assets, W=128, transaction costs) at a lock-step-able env count, plus small /
+    odd shapes (unaligned chunk tails -> plain-store path, A = 32 full warp, high sigma -> margin calls and
+    bankruptcies across assets).  No reference exists for A > 1: the oracle's multi-asset code is the one
+    proven equal to the reference at A = 1 (tests/test_oracle_golden.py)."""
+    from oracle import oracle as orc
+    from finenvs_b200.data import loader
+
+    bars = 40
+    prices, seg_start, seg_len = _portfolio_series(A, W, days=10 + W // bars, bars=bars, sigma=sigma, seed=A * 1000 + W)
+    series = loader.stage_series(prices, seg_start, seg_len, W, "cuda:0", dtype, keep_logret64=True)
+    assert series.num_assets == A
+    env = _env(series, num_envs=N, seed=5, random_reset="all", random_offset=True, obs_dtype=dtype, track_stats=True)
+    assert env.num_acts == A and env.num_obs == 5 * A
+    fs = orc.series_from_prices(prices, seg_start, seg_len, W, logret=series.logret64.cpu().numpy())
+    ref = orc.OracleEnv(fs, num_envs=N, seed=5, reset_mode=2, random_offset=True, out_f64=dtype == torch.float64)
+    rng = np.random.default_rng(A + W)
+
+    def act(r, n):
+        a = r.uniform(-1, 1, (n, A))
+        m = r.uniform(0, 1, (n, A)) < 0.4
+        a[m] = -np.abs(a[m])
+        return a.astype(np.float32)
+
+    ad = CudaAdapter(env)
+    assert_bits_equal(ref.reset(), ad.reset(), "reset obs")
+    n_done = 0
+    for t in range(90):
+        a = act(rng, N)
+        o_ref, r_ref, d_ref, _ = ref.step(a)
+        o, r, d, _ = ad.step(a)
+        assert_bits_equal(d_ref, d, f"dones t={t}")
+        st = ad.state()
+        for key in ("seg", "ptr", "cash"):
+            assert_bits_equal(getattr(ref, key), st[key], f"{key} t={t}")
+        for key in ("long_sh", "short_sh", "margin"):
+            assert_bits_equal(getattr(ref, key).reshape(-1), st[key], f"{key} t={t}")
+        assert_bits_equal(r_ref, r, f"rewards t={t}")
+        assert_bits_equal(o_ref, o, f"obs t={t}")
+        n_done += int(d_ref.sum())
+    assert n_done > 0 and int(env.stats()["n_done"].item()) == n_done

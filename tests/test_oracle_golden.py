@@ -8,12 +8,13 @@ from parity_utils import golden_traces, load_trace, oracle_state, replay_trace, 
 
 
 @pytest.mark.parametrize("name", golden_traces())
-@pytest.mark.parametrize("out_f64", [True, False])
-def test_oracle_replays_reference_trace(name, out_f64):
+@pytest.mark.parametrize("out_f64,multi", [(True, False), (False, False), (True, True)])
+def test_oracle_replays_reference_trace(name, out_f64, multi):
+    """multi=True runs the multi-asset extension's code path at A = 1: it must still be the reference."""
     z = load_trace(name)
     fs = trace_series(z)
     env = orc.OracleEnv(fs, num_envs=len(z["seg_init"]), evaluate=bool(z["evaluate"]), seed=int(z["seed"]),
-                        seg_init=z["seg_init"], out_f64=out_f64)
+                        seg_init=z["seg_init"], out_f64=out_f64, force_multi=multi)
     replay_trace(z, env, lambda: oracle_state(env), out_f64, name)
     # the redraws the reference consumed are the oracle's own Philox draws
     for step, kind, seg in z["draw_log"]:
