@@ -62,6 +62,8 @@ class TimeSeriesEnv(BaseObject):
         total_envs: Optional[int] = None,
         track_stats: bool = False,
         variant: str = "auto",
+        flat_obs: bool = False,
+        num_eval_envs: Optional[int] = None,
     ):
         """Reference arguments: :15-29.  Extensions:
 
@@ -77,7 +79,11 @@ class TimeSeriesEnv(BaseObject):
                       population (multi-GPU); draws are keyed by global id, so results do not
                       depend on the sharding.
         track_stats   accumulate episode count / return / length on the device (stats()).
-        variant       "auto" | "tile" | "direct" kernel variant.
+        variant       "auto" | "tile" | "direct" | "portfolio" kernel variant.
+        flat_obs      return observations as (N, W*num_obs) — the 2-D input the ES agent's ParallelMLP needs
+                      (parallel_mlp.py:98-103); same memory, only the shape differs.
+        num_eval_envs reported in get_env_args() for the ES agent (evo_agent.py:53); the last
+                      num_eval_envs envs are the evaluation envs by the reference's convention.
         """
         if obs_dtype not in (torch.float32, torch.float64):
             raise ValueError("obs_dtype must be torch.float32 or torch.float64")
@@ -120,6 +126,8 @@ class TimeSeriesEnv(BaseObject):
         self.random_offset = bool(random_offset)
         self.seed = int(torch.initial_seed() if seed is None else seed) & 0xFFFFFFFFFFFFFFFF
         self.track_stats = bool(track_stats)
+        self.flat_obs = bool(flat_obs)
+        self.num_eval_envs = num_eval_envs
         self.set_environment_params(num_envs, env_id_base, total_envs, _VARIANTS[variant])
 
     # ------------------------------------------------------------------ metadata (:218-243) ----
@@ -134,13 +142,16 @@ class TimeSeriesEnv(BaseObject):
         )
 
     def get_env_args(self) -> Dict:
-        return {
+        env_args = {
             "env_name": self.instrument_name,
             "num_envs": self.num_envs,
-            "num_observations": self.num_obs,
+            "num_observations": self.num_obs * (self.num_intervals if self.flat_obs else 1),
             "num_actions": self.num_acts,
             "sequence_length": self.num_intervals,
         }
+        if self.num_eval_envs is not None:
+            env_args["num_eval_envs"] = self.num_eval_envs
+        return env_args
 
     # ------------------------------------------------------------------ state (:245-275) -------
     def set_environment_params(self, num_envs=None, env_id_base=0, total_envs=None, variant=0) -> None:
@@ -245,7 +256,9 @@ class TimeSeriesEnv(BaseObject):
 
     def _new_obs(self) -> torch.Tensor:
         # a fresh tensor every call: the PPO buffer keeps references to past observations (buffer.py:44-56)
-        return torch.empty((self.num_envs, self.num_intervals, self.num_obs), dtype=self.obs_dtype, device=self._dev)
+        shape = ((self.num_envs, self.num_intervals * self.num_obs) if self.flat_obs
+                 else (self.num_envs, self.num_intervals, self.num_obs))
+        return torch.empty(shape, dtype=self.obs_dtype, device=self._dev)
 
     def reset(self) -> torch.Tensor:
         """:423-435 — materialises the current observation; touches no state (reference semantics)."""

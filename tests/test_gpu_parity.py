@@ -314,3 +314,134 @@ def test_portfolio_env_vs_oracle(A, W, N, sigma, dtype):
         assert_bits_equal(o_ref, o, f"obs t={t}")
         n_done += int(d_ref.sum())
     assert n_done > 0 and int(env.stats()["n_done"].item()) == n_done
+
+
+# ------------------------------------------------------------------ BASELINE full sizes -------------
+def _check_obs_properties(env, obs, ptr_before_reset, seg_before_reset):
+    """Size-independent properties of one step's observation: columns 0..3 are exactly the log-return window
+    [ptr, ptr+W) of the env's segment (gathered here with torch indexing), column 4 is constant over the window."""
+    W, A = env.num_intervals, env.num_assets
+    s = env.series
+    n = obs.shape[0]
+    o = obs.view(n, W, A, 5)
+    row0 = s.seg_start[seg_before_reset.long()] + ptr_before_reset.long()
+    idx = torch.randint(0, n, (4096,), device=obs.device)
+    rows = row0[idx, None] + torch.arange(W, device=obs.device)[None, :]
+    want = s.logret.view(s.num_rows, A, 4)[rows]                     # (4096, W, A, 4)
+    assert torch.equal(o[idx][..., :4], want)
+    assert torch.equal(o[..., 4], o[:, :1, :, 4].expand(-1, W, -1))
+
+
+def test_config2_full_size_1M_envs():
+    """BASELINE config 2 at full size: 1 Mi envs, W=60.  Three steps of the FULL population against the oracle
+    (state, rewards, dones exact; obs through its gather property) and a 65 536-env slice in lock-step for
+    2x252 steps (every env auto-resets at least twice)."""
+    from oracle import oracle as orc
+    from finenvs_b200.data import loader
+
+    W, N = 60, 1 << 20
+    prices, seg_start, seg_len = _c1_series(W)
+    series = loader.stage_series(prices, seg_start, seg_len, W, "cuda:0", torch.float32, keep_logret64=True)
+    fs = orc.series_from_prices(prices, seg_start, seg_len, W, logret=series.logret64.cpu().numpy())
+    env = _env(series, num_envs=N, seed=42, random_reset="all", random_offset=True, track_stats=True)
+    ref = orc.OracleEnv(fs, num_envs=N, seed=42, reset_mode=2, random_offset=True, out_f64=False)
+    g = torch.Generator().manual_seed(0)
+    total_done = 0
+    for t in range(3):
+        a = torch.rand((N, 1), generator=g) * 2 - 1
+        ptr0, seg0 = env._ptr.clone() + 1, env._seg.clone()
+        obs, r, d, _ = env.step(a.cuda())
+        _, r_ref, d_ref, _ = ref.step(a.numpy(), want_obs=False)
+        assert np.array_equal(d.cpu().numpy(), d_ref) and np.array_equal(r.cpu().numpy(), r_ref)
+        for key, t_gpu in (("seg", env._seg), ("ptr", env._ptr), ("cash", env._cash), ("long_sh", env._long),
+                           ("short_sh", env._short), ("margin", env._margin)):
+            assert np.array_equal(t_gpu.cpu().numpy(), getattr(ref, key)), key
+        _check_obs_properties(env, obs, ptr0, seg0)
+        assert int((env._long * env._short).abs().sum()) == 0          # never long and short at once (:311-314)
+        assert bool((env._ptr + W < series.seg_len[env._seg.long()]).all())  # a bar always remains to step onto
+        total_done += int(d_ref.sum())
+    assert int(env.stats()["n_done"].item()) == total_done
+    # slice in lock-step: global ids [base, base+65536) of the same population (shard-invariant draws)
+    base, n = 300_000, 65536
+    sl = _env(series, num_envs=n, env_id_base=base, total_envs=N, seed=42, random_reset="all", random_offset=True)
+    ref_sl = orc.OracleEnv(fs, num_envs=n, env_id_base=base, total_envs=N, seed=42, reset_mode=2, random_offset=True,
+                           out_f64=False)
+    n_done = _lockstep(sl, ref_sl, 2 * 252, np.random.default_rng(3), obs_every=101)
+    assert n_done >= 2 * n
+
+
+def test_config4_minute_bars_8M_population_shard():
+    """BASELINE config 4: 10 M-row minute-bar series, 8 Mi envs with random start offsets, env-sharded over 8 GPUs.
+    This GPU holds shard 5 (1 Mi envs); it must equal the oracle run of the same global ids."""
+    from oracle import oracle as orc
+    from finenvs_b200.data import loader
+
+    W, T, bars = 60, 10_000_000, 390
+    rng = np.random.default_rng(20260101)
+    prices = np.round(gbm_ohlc(rng, T, 0.0005), 4)
+    seg_start, seg_len = loader.regular_segments(T, bars, W)
+    series = loader.stage_series(prices, seg_start, seg_len, W, "cuda:0", torch.float32, keep_logret64=True)
+    assert series.num_segments == 25640 and series.nbytes() > 126e6    # larger than L2
+    fs = orc.series_from_prices(prices, seg_start, seg_len, W, logret=series.logret64.cpu().numpy())
+    total, n, rank = 8 << 20, 1 << 20, 5
+    env = _env(series, num_envs=n, env_id_base=rank * n, total_envs=total, seed=7, random_reset="all", random_offset=True)
+    ref = orc.OracleEnv(fs, num_envs=n, env_id_base=rank * n, total_envs=total, seed=7, reset_mode=2, random_offset=True,
+                        out_f64=False)
+    assert np.array_equal(env._seg.cpu().numpy(), ref.seg) and np.array_equal(env._ptr.cpu().numpy(), ref.ptr)
+    assert len(np.unique(ref.ptr)) == bars                              # every start offset is drawn
+    g = torch.Generator().manual_seed(1)
+    for t in range(4):
+        a = torch.rand((n, 1), generator=g) * 2 - 1
+        ptr0, seg0 = env._ptr.clone() + 1, env._seg.clone()
+        obs, r, d, _ = env.step(a.cuda())
+        _, r_ref, d_ref, _ = ref.step(a.numpy(), want_obs=False)
+        assert np.array_equal(d.cpu().numpy(), d_ref) and np.array_equal(r.cpu().numpy(), r_ref)
+        assert np.array_equal(env._seg.cpu().numpy(), ref.seg) and np.array_equal(env._ptr.cpu().numpy(), ref.ptr)
+        assert np.array_equal(env._cash.cpu().numpy(), ref.cash)
+        _check_obs_properties(env, obs, ptr0, seg0)
+        assert d_ref.sum() > 0                                          # offsets spread the episode ends
+
+
+def test_config3_full_size_portfolio():
+    """BASELINE config 3 at full size: 30 assets, 65 536 envs, W=128 (obs is 5 GB per step)."""
+    from oracle import oracle as orc
+    from finenvs_b200.data import loader
+
+    A, W, N = 30, 128, 65536
+    prices, seg_start, seg_len = _portfolio_series(A, W, days=40, bars=252, sigma=0.01, seed=33)
+    series = loader.stage_series(prices, seg_start, seg_len, W, "cuda:0", torch.float32, keep_logret64=True)
+    fs = orc.series_from_prices(prices, seg_start, seg_len, W, logret=series.logret64.cpu().numpy())
+    env = _env(series, num_envs=N, seed=8, random_reset="all", random_offset=True)
+    ref = orc.OracleEnv(fs, num_envs=N, seed=8, reset_mode=2, random_offset=True, out_f64=False)
+    g = torch.Generator().manual_seed(2)
+    for t in range(3):
+        a = torch.rand((N, A), generator=g) * 2 - 1
+        ptr0, seg0 = env._ptr.clone() + 1, env._seg.clone()
+        obs, r, d, _ = env.step(a.cuda())
+        _, r_ref, d_ref, _ = ref.step(a.numpy(), want_obs=False)
+        assert np.array_equal(d.cpu().numpy(), d_ref) and np.array_equal(r.cpu().numpy(), r_ref)
+        assert np.array_equal(env._cash.cpu().numpy(), ref.cash)
+        assert np.array_equal(env._margin.cpu().numpy(), ref.margin.reshape(-1))
+        assert np.array_equal(env._long.cpu().numpy(), ref.long_sh.reshape(-1))
+        _check_obs_properties(env, obs, ptr0, seg0)
+        del obs
+
+
+def test_flat_obs_and_es_env_args():
+    """The ES agent needs 2-D fp32 observations, num_eval_envs in the env args and reset_all()
+    (evo_agent.py:49-65, parallel_mlp.py:98-103, ES_MLP_Isaac_Gym.py:38)."""
+    from finenvs_b200.data import loader
+
+    W = 16
+    prices, seg_start, seg_len = _c1_series(W, days=64, bars=40, sigma=0.03)
+    series = loader.stage_series(prices, seg_start, seg_len, W, "cuda:0", torch.float32)
+    a = _env(series, num_envs=500, seed=1, random_reset="all")
+    b = _env(series, num_envs=500, seed=1, random_reset="all", flat_obs=True, num_eval_envs=12)
+    args = b.get_env_args()
+    assert args["num_observations"] == W * 5 and args["num_eval_envs"] == 12 and "num_eval_envs" not in a.get_env_args()
+    act = torch.rand((500, 1), device="cuda") * 2 - 1
+    oa, _, _, _ = a.step(act)
+    ob, _, _, _ = b.step(act)
+    assert ob.shape == (500, W * 5) and ob.dtype == torch.float32 and torch.equal(oa.view(500, -1), ob)
+    o0 = b.reset_all()
+    assert o0.shape == (500, W * 5) and int(b._ptr.abs().sum()) == 0 and float(b._cash.min()) == 10000.0
