@@ -212,7 +212,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"])
     ap.add_argument("--envs", type=int, default=None, help="envs per GPU (default: 1 Mi; c3: 65536)")
     ap.add_argument("--window", type=int, default=None, help="default 60; c3: 128")
-    ap.add_argument("--variant", default="auto", choices=["auto", "tile", "direct"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "tile", "direct", "pipe"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -325,7 +325,7 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": f"of {peak_src}",
                      "algorithmic_bytes_per_env_step": algorithmic_bytes_per_env_step(W, A),
-                     "kernel": "fe_portfolio_kernel<float,false>" if A > 1 else "fe_tile_kernel<float,false>",
+                     "kernel": env.kernel_name(),
                      "kernel_ms": kernel_s * 1e3},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * N * A, "d2h_bytes_per_step": 8 * N,
                 "ms_per_step": e2e_ms / args.steps, "api": "TimeSeriesEnv.step_host -> fe_step_host (pinned host buffers)"},

@@ -10,10 +10,11 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfinenvs_b200.so")
+# FINENVS_B200_LIB: alternative build of the same library (kernel tuning experiments only)
+LIB_PATH = os.environ.get("FINENVS_B200_LIB") or os.path.join(_HERE, "libfinenvs_b200.so")
 
 RESET_KEEP, RESET_LAST, RESET_ALL = 0, 1, 2
-VARIANT_AUTO, VARIANT_TILE, VARIANT_DIRECT, VARIANT_PORTFOLIO = 0, 1, 2, 3
+VARIANT_AUTO, VARIANT_TILE, VARIANT_DIRECT, VARIANT_PORTFOLIO, VARIANT_PIPE = 0, 1, 2, 3, 4
 ABI_VERSION = 1
 
 
@@ -66,6 +67,8 @@ _PROTOTYPES = {
     "fe_version": (C.c_int, []),
     "fe_error_string": (C.c_char_p, [C.c_int]),
     "fe_tile_envs": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
+    "fe_pipe_envs": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
+    "fe_step_kernel_name": (C.c_char_p, [C.POINTER(FeParams)]),
     "fe_log_returns": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fe_effective_len": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                    C.c_void_p]),

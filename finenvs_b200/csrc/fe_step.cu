@@ -405,6 +405,237 @@ fe_tile_kernel(const FeParams p, const FeSeries s, const FeState st, const Const
 }
 
 // ------------------------------------------------------------------------------------------
+// pipe variant: persistent, warp-specialised (the fast path; windows up to 512 rows)
+//
+// One block per SM loops over tiles of TE consecutive envs.  Roles:
+//   bookkeeper warps (kPipeBook): one lane per env at full lane utilisation; run the per-env arithmetic and
+//       publish {row0, position feature} of a tile into a ring of Q descriptors (mbarriers desc_full /
+//       desc_free).  They run up to Q tiles ahead, so their load -> lookup -> load -> arithmetic latency
+//       chain is off the critical path.
+//   mover warps (kPipeMove): gather the tile's window rows with coalesced 16-byte loads straight into
+//       registers (RPT rows per thread, the loads of tile t+1 are issued before tile t is written, so
+//       their L2/HBM latency hides behind a whole tile of work), interleave the position feature while
+//       storing into the out ring (conflict-free stride-5 STS), and one thread issues ONE bulk async store
+//       (UBLKCP.G.S) per tile; up to S_OUT stores stay in flight.
+// History (profiles/r01_pipe_*.txt): a first version fetched every env's window with its own bulk async
+// copy into an in-ring; ncu showed the block pinned on the copy-issue loop — one UBLKCP per ~85 cycles
+// per SM whatever the stage counts (7085 copies per SM per step => 0.32 ms floor), the same wall the
+// tile variant hits.  Register gathers have no such per-copy cost and halve the shared-memory traffic.
+// ------------------------------------------------------------------------------------------
+#ifndef FE_PIPE_BOOK
+#define FE_PIPE_BOOK 6
+#endif
+#ifndef FE_PIPE_MOVE
+#define FE_PIPE_MOVE 8
+#endif
+#ifndef FE_PIPE_SOUT
+#define FE_PIPE_SOUT 2
+#endif
+#ifndef FE_PIPE_SIN
+#define FE_PIPE_SIN 4   /* in-ring stages of the "stream" flavour (series larger than L2) */
+#endif
+#ifndef FE_PIPE_RPT
+#define FE_PIPE_RPT 8   /* f32 rows per mover thread per tile (f64: half) */
+#endif
+constexpr int kPipeBook = FE_PIPE_BOOK;
+constexpr int kPipeMove = FE_PIPE_MOVE;
+constexpr int kPipeThreads = (kPipeBook + kPipeMove) * 32;
+constexpr int kMovers = kPipeMove * 32;
+constexpr int kPipeQ = 8;                // descriptor ring depth
+constexpr int kPipeSOut = FE_PIPE_SOUT;  // out-tile stages
+// Two flavours, chosen per launch from the size of the log-return table (pick_pipe_stages):
+//   kSIn == 0  "cached": the table is L2-resident, one tile of register prefetch covers the L2 latency and the
+//              rows never touch shared memory on the way in (measured c2: 0.28 ms vs 0.35 ms for kSIn == 3);
+//   kSIn  > 0  "stream": the table lives in HBM; rows arrive through an in-ring of kSIn stages filled with
+//              16-byte cp.async (LDGSTS), ~kSIn x 30 KB in flight per SM (measured c4: 0.376 ms vs 0.43 ms).
+constexpr int kPipeSInStream = FE_PIPE_SIN;
+template <typename OutT> struct PipeRows { static constexpr int value = sizeof(OutT) == 4 ? FE_PIPE_RPT : (FE_PIPE_RPT + 1) / 2; }; // rows / thread / tile
+
+// smem: [mbarriers desc_full[Q], desc_free[Q], in_full[S_IN]] (256 B) [descriptors Q x TE x (8 + 8) B]
+//       [in ring S_IN x TE*W*4 OutT] [out ring S_OUT x TE*W*5 OutT]
+template <typename OutT> __host__ __device__ inline size_t pipe_smem_bytes(int TE, int W, int sin) {
+    return 256 + (size_t)kPipeQ * TE * 16 + (size_t)TE * W * sizeof(OutT) * (4 * sin + 5 * kPipeSOut);
+}
+// 16-byte async copy global -> shared (LDGSTS), and "arrive on the mbarrier once my copies have landed"
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ Row4<float> ldg_row(const Row4<float> *p) {
+    Row4<float> r;
+    r.v = __ldg(reinterpret_cast<const float4 *>(p));
+    return r;
+}
+__device__ __forceinline__ Row4<double> ldg_row(const Row4<double> *p) {
+    Row4<double> r;
+    r.a = __ldg(reinterpret_cast<const double2 *>(p));
+    r.b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+    return r;
+}
+
+template <typename OutT, bool kObserve, int kPipeSIn>
+__global__ void __launch_bounds__(kPipeThreads, 1)
+fe_pipe_kernel(const FeParams p, const FeSeries s, const FeState st, const Consts k, const float *__restrict__ actions,
+               OutT *__restrict__ obs, OutT *__restrict__ rewards, int32_t *__restrict__ dones, FeStats *stats,
+               const uint64_t step, const int TE) {
+    constexpr int RPT = PipeRows<OutT>::value;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int W = p.window;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t ntiles_all = (p.num_envs + TE - 1) / TE;
+    const int ntiles = (int)((ntiles_all - blockIdx.x + gridDim.x - 1) / gridDim.x); // tiles blockIdx.x, +gridDim.x, ...
+    const uint32_t bars = smem_u32(smem);
+    auto desc_full = [&](int q) { return bars + 8u * q; };
+    auto desc_free = [&](int q) { return bars + 8u * (kPipeQ + q); };
+    auto in_full = [&](int si) { return bars + 8u * (2 * kPipeQ + si); };
+    int64_t *d_row0 = reinterpret_cast<int64_t *>(smem + 256);                       // [Q][TE]
+    double *d_pf = reinterpret_cast<double *>(smem + 256 + (size_t)kPipeQ * TE * 8); // [Q][TE], OutT in the low bytes
+    const size_t in_stage = (size_t)TE * W * 4 * sizeof(OutT), out_stage = (size_t)TE * W * 5 * sizeof(OutT);
+    unsigned char *in_ring = smem + 256 + (size_t)kPipeQ * TE * 16;
+    unsigned char *out_ring = in_ring + kPipeSIn * in_stage;
+
+    if (tid == 0) {
+        for (int q = 0; q < kPipeQ; ++q) { mbar_init(desc_full(q), 1); mbar_init(desc_free(q), 1); }
+        for (int si = 0; si < kPipeSIn; ++si) mbar_init(in_full(si), kMovers);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp < kPipeBook) {
+        // ------------------------------------------------------------------ bookkeepers
+        for (int t = warp; t < ntiles; t += kPipeBook) {
+            const int q = t % kPipeQ;
+            mbar_wait(desc_free(q), ((t / kPipeQ) & 1) ^ 1); // first lap passes immediately
+            const int64_t env0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TE;
+            const int nvalid = (int)min((int64_t)TE, p.num_envs - env0);
+            EnvResult r;
+            r.done = 0; r.newly_terminated = 0; r.fin_return = 0.0; r.fin_len = 0; r.row0 = 0; r.posfeat = 0.0;
+            const bool active = lane < nvalid;
+            if (active) {
+                const int64_t i = env0 + lane;
+                if (kObserve) r = env_observe(p, s, st, k, i);
+                else r = env_step<OutT>(p, s, st, k, i, actions, rewards, dones, stats != nullptr, step);
+                d_row0[q * TE + lane] = r.row0;
+                reinterpret_cast<OutT *>(d_pf + q * TE)[lane] = (OutT)r.posfeat;
+            }
+            if (!kObserve) accumulate_stats(stats, r, active);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(desc_full(q)); // release: descriptor visible to the movers
+        }
+    } else {
+        // ------------------------------------------------------------------ movers
+        const int mtid = tid - kPipeBook * 32;
+        const float invW = 1.0f / (float)W;
+        const Row4<OutT> *series_rows = reinterpret_cast<const Row4<OutT> *>(s.logret);
+        auto tile_rows = [&](int t) {
+            const int64_t env0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TE;
+            return (int)min((int64_t)TE, p.num_envs - env0) * W;
+        };
+        // fetch tile t's rows: row r of the tile = env r / W, window row r % W.  Either straight into registers
+        // (kPipeSIn == 0) or with 16-byte async copies into in-ring stage t % S_IN, arriving on in_full when landed.
+        auto gather = [&](int t, Row4<OutT>(&buf)[RPT]) {
+            const int q = t % kPipeQ;
+            mbar_wait(desc_full(q), (t / kPipeQ) & 1);
+            const int nrows = tile_rows(t);
+            const uint32_t stage = kPipeSIn > 0 ? smem_u32(in_ring + (t % (kPipeSIn > 0 ? kPipeSIn : 1)) * in_stage) : 0u;
+#pragma unroll
+            for (int u = 0; u < RPT; ++u) {
+                const int r = mtid + u * kMovers;
+                if (r < nrows) {
+                    const int e = __float2int_rz(((float)r + 0.5f) * invW);
+                    const Row4<OutT> *src = series_rows + d_row0[q * TE + e] + (r - e * W);
+                    if constexpr (kPipeSIn == 0) {
+                        buf[u] = ldg_row(src);
+                    } else {
+                        cp_async16(stage + (uint32_t)r * sizeof(Row4<OutT>), src);
+                        if constexpr (sizeof(OutT) == 8)
+                            cp_async16(stage + (uint32_t)r * sizeof(Row4<OutT>) + 16, reinterpret_cast<const char *>(src) + 16);
+                    }
+                }
+            }
+            if constexpr (kPipeSIn > 0) cp_async_arrive_noinc(in_full(t % (kPipeSIn > 0 ? kPipeSIn : 1)));
+        };
+        Row4<OutT> cur[RPT], nxt[RPT];
+        constexpr int kAhead = kPipeSIn > 0 ? kPipeSIn : 1;
+        if constexpr (kPipeSIn == 0) {
+            if (ntiles > 0) gather(0, cur);
+        } else {
+            for (int t = 0; t < kAhead && t < ntiles; ++t) gather(t, nxt);
+        }
+        for (int t = 0; t < ntiles; ++t) {
+            const int q = t % kPipeQ, so = t % kPipeSOut;
+            const int64_t env0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TE;
+            const int nrows = tile_rows(t);
+            if constexpr (kPipeSIn == 0) {
+                if (t + 1 < ntiles) gather(t + 1, nxt); // in flight while this tile is written
+            } else {
+                mbar_wait(in_full(t % kAhead), (t / kAhead) & 1);
+                const Row4<OutT> *in_rows = reinterpret_cast<const Row4<OutT> *>(in_ring + (t % kAhead) * in_stage);
+#pragma unroll
+                for (int u = 0; u < RPT; ++u) {
+                    const int r = mtid + u * kMovers;
+                    if (r < nrows) cur[u] = in_rows[r];
+                }
+            }
+            if (t >= kPipeSOut) { // the store that last used out[so] must have finished reading shared memory
+                if (mtid == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPipeSOut - 1) : "memory");
+                named_bar_sync(1, kMovers);
+            }
+            OutT *out_tile = reinterpret_cast<OutT *>(out_ring + so * out_stage);
+            const OutT *pf = reinterpret_cast<const OutT *>(d_pf + q * TE);
+#pragma unroll
+            for (int u = 0; u < RPT; ++u) {
+                const int r = mtid + u * kMovers;
+                if (r < nrows) {
+                    const int e = __float2int_rz(((float)r + 0.5f) * invW);
+                    OutT *o = out_tile + (size_t)r * 5;
+                    if constexpr (sizeof(OutT) == 4) {
+                        o[0] = cur[u].v.x; o[1] = cur[u].v.y; o[2] = cur[u].v.z; o[3] = cur[u].v.w;
+                    } else {
+                        o[0] = cur[u].a.x; o[1] = cur[u].a.y; o[2] = cur[u].b.x; o[3] = cur[u].b.y;
+                    }
+                    o[4] = pf[e];
+                }
+            }
+            const size_t out_bytes = (size_t)nrows * 5 * sizeof(OutT);
+            OutT *dst = obs + (size_t)env0 * W * 5;
+            if ((out_bytes & 15) == 0) {
+                fence_proxy_async_smem();
+                named_bar_sync(1, kMovers); // out tile complete, descriptor consumed
+                if (mtid == 0) {
+                    bulk_store(dst, smem_u32(out_tile), (uint32_t)out_bytes);
+                    bulk_commit();
+                }
+            } else { // ragged last tile
+                named_bar_sync(1, kMovers);
+                for (int f = mtid; f < nrows * 5; f += kMovers) dst[f] = out_tile[f];
+                named_bar_sync(1, kMovers);
+            }
+            if constexpr (kPipeSIn == 0) {
+                if (mtid == 0) mbar_arrive(desc_free(q));
+#pragma unroll
+                for (int u = 0; u < RPT; ++u) cur[u] = nxt[u];
+            } else {
+                // the barrier above also means every mover finished reading in-stage t % S_IN: refill it, and only
+                // then release the descriptor (the refill of tile t+S_IN reads ITS descriptor, not this one)
+                if (mtid == 0) mbar_arrive(desc_free(q));
+                if (t + kAhead < ntiles) gather(t + kAhead, nxt);
+            }
+        }
+        if (mtid == 0) bulk_wait_read_all();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // direct variant: any window; thread-per-env bookkeeping, then warp-per-env copy
 // ------------------------------------------------------------------------------------------
 template <typename OutT, bool kObserve>
@@ -820,6 +1051,22 @@ int pick_tile_envs(int W, bool f64, int *threads_out = nullptr) {
     return (int)e;
 }
 
+// envs per tile of the pipe variant: up to 32 (one bookkeeper lane each), a multiple of 4 (16-byte store
+// granularity), with TE*W rows fitting the movers' register staging; 0 = window too large, use the tile variant
+int pick_pipe_envs(int W, bool f64, int sin) {
+    const int max_rows = kMovers * (f64 ? PipeRows<double>::value : PipeRows<float>::value);
+    int te = (max_rows / W) & ~3;
+    if (te > 32) te = 32;
+    while (te >= 4 && (f64 ? pipe_smem_bytes<double>(te, W, sin) : pipe_smem_bytes<float>(te, W, sin)) > (size_t)kSmemMax) te -= 4;
+    return te < 4 ? 0 : te;
+}
+// in-ring stages: 0 ("cached" flavour) while the log-return table is comfortably L2-resident (126 MB L2, shared
+// with the observation stream passing through it), else the "stream" flavour
+int pick_pipe_stages(const FeParams &p, bool f64) {
+    const size_t table = (size_t)p.num_rows * p.num_assets * 4 * (f64 ? 8 : 4);
+    return table <= ((size_t)48 << 20) ? 0 : kPipeSInStream;
+}
+
 // tuning overrides (sweeps only): FE_TILE_ENVS (multiple of 4), FE_TILE_THREADS (multiple of 32, <= 128)
 int env_override(const char *name) {
     const char *v = getenv(name);
@@ -849,6 +1096,35 @@ int launch(const FeParams &p, const FeSeries &s, const FeState &st, const float 
         kern<<<(unsigned)p.num_envs, kPortThreads, smem, stream>>>(p, s, st, k, actions, (OutT *)obs, (OutT *)rewards,
                                                                   dones, stats, step, CH);
         return (int)cudaGetLastError();
+    }
+    static const int no_pipe = env_override("FE_NO_PIPE"); // sweeps: make "auto" fall through to the tile variant
+    if (p.variant == FE_VARIANT_PIPE || (p.variant == FE_VARIANT_AUTO && !no_pipe)) {
+        static const int ov_sin = env_override("FE_PIPE_FLAVOUR"); // sweeps: 1 = cached, 2 = stream
+        int sin = ov_sin == 1 ? 0 : ov_sin == 2 ? kPipeSInStream : pick_pipe_stages(p, sizeof(OutT) == 8);
+        int TE = pick_pipe_envs(p.window, sizeof(OutT) == 8, sin);
+        // small populations: the persistent grid needs a few tiles per SM to hide its prologue; the tile variant's
+        // many tiny blocks are the better shape there
+        const bool worth = p.num_envs >= (int64_t)4 * 148 * 32;
+        if (TE == 0 && p.variant == FE_VARIANT_PIPE) return FE_ESMEM;
+        if (TE > 0 && (worth || p.variant == FE_VARIANT_PIPE)) {
+            if ((uintptr_t)obs & 15) return FE_EALIGN;
+            auto kern = sin == 0 ? fe_pipe_kernel<OutT, kObserve, 0> : fe_pipe_kernel<OutT, kObserve, kPipeSInStream>;
+            static bool configured[16][2] = {{false}};
+            static int num_sms[16] = {0};
+            const int dev = p.device & 15;
+            if (!configured[dev][sin != 0]) {
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+                if (e != cudaSuccess) return (int)e;
+                e = cudaDeviceGetAttribute(&num_sms[dev], cudaDevAttrMultiProcessorCount, p.device);
+                if (e != cudaSuccess) return (int)e;
+                configured[dev][sin != 0] = true;
+            }
+            const int64_t ntiles = (p.num_envs + TE - 1) / TE;
+            const unsigned blocks = (unsigned)(ntiles < num_sms[dev] ? ntiles : num_sms[dev]);
+            kern<<<blocks, kPipeThreads, pipe_smem_bytes<OutT>(TE, p.window, sin), stream>>>(
+                p, s, st, k, actions, (OutT *)obs, (OutT *)rewards, dones, stats, step, TE);
+            return (int)cudaGetLastError();
+        }
     }
     int threads = kThreads;
     int E = p.variant == FE_VARIANT_DIRECT ? 0 : pick_tile_envs(p.window, sizeof(OutT) == 8, &threads);
@@ -892,6 +1168,27 @@ int set_device(int device) {
     return 0;
 }
 
+// side streams of fe_step_host (created once per device, never destroyed: they live as long as the process)
+constexpr int kHostStreams = 3;
+struct HostPipe {
+    cudaStream_t s[kHostStreams];
+    cudaEvent_t start, done[kHostStreams];
+    bool ready;
+};
+HostPipe *host_pipe(int device) {
+    static HostPipe pipes[16];
+    HostPipe *hp = &pipes[device & 15];
+    if (!hp->ready) {
+        for (int k = 0; k < kHostStreams; ++k) {
+            if (cudaStreamCreateWithFlags(&hp->s[k], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&hp->done[k], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        }
+        if (cudaEventCreateWithFlags(&hp->start, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        hp->ready = true;
+    }
+    return hp;
+}
+
 } // namespace
 
 extern "C" {
@@ -911,6 +1208,26 @@ const char *fe_error_string(int code) {
 int fe_tile_envs(int32_t window, int32_t out_f64, int32_t device) {
     (void)device;
     return window > 0 ? pick_tile_envs(window, out_f64 != 0) : 0;
+}
+
+int fe_pipe_envs(int32_t window, int32_t out_f64, int32_t stream_flavour) {
+    return window > 0 ? pick_pipe_envs(window, out_f64 != 0, stream_flavour ? kPipeSInStream : 0) : 0;
+}
+
+const char *fe_step_kernel_name(const FeParams *p) {
+    if (!p) return "";
+    const bool f64 = p->out_f64 != 0;
+    if (p->num_assets > 1 || p->variant == FE_VARIANT_PORTFOLIO) return f64 ? "fe_portfolio_kernel<double>" : "fe_portfolio_kernel<float>";
+    if (p->variant == FE_VARIANT_PIPE || (p->variant == FE_VARIANT_AUTO && !env_override("FE_NO_PIPE"))) {
+        const int ov = env_override("FE_PIPE_FLAVOUR");
+        const int sin = ov == 1 ? 0 : ov == 2 ? kPipeSInStream : pick_pipe_stages(*p, f64);
+        const int TE = pick_pipe_envs(p->window, f64, sin);
+        if (TE > 0 && (p->variant == FE_VARIANT_PIPE || p->num_envs >= (int64_t)4 * 148 * 32))
+            return sin == 0 ? (f64 ? "fe_pipe_kernel<double,cached>" : "fe_pipe_kernel<float,cached>")
+                            : (f64 ? "fe_pipe_kernel<double,stream>" : "fe_pipe_kernel<float,stream>");
+    }
+    if (p->variant != FE_VARIANT_DIRECT && pick_tile_envs(p->window, f64) > 0) return f64 ? "fe_tile_kernel<double>" : "fe_tile_kernel<float>";
+    return f64 ? "fe_direct_kernel<double>" : "fe_direct_kernel<float>";
 }
 
 int fe_log_returns(const double *prices_dev, int64_t num_rows, int32_t num_assets, double *logret64_dev,
@@ -953,22 +1270,68 @@ int fe_step(const FeParams *p, const FeSeries *s, const FeState *st, const float
                                              step_counter, (cudaStream_t)stream);
 }
 
+// Host-buffer step, pipelined: the envs are cut into chunks (multiples of 1024 envs, so every chunk's slice of
+// every array keeps its alignment); chunk c's action upload, kernel and result download run on side stream
+// c % kHostStreams, so the upload of chunk c+1 and the download of chunk c-1 overlap the kernel of chunk c
+// (two copy engines + SMs busy at once).  Redraws are keyed by global env id, so chunking changes no result.
 int fe_step_host(const FeParams *p, const FeSeries *s, const FeState *st, const float *actions_host, float *actions_dev,
                  void *obs_dev, void *rewards_dev, int32_t *dones_dev, void *rewards_host, int32_t *dones_host,
                  FeStats *stats_dev, uint64_t step_counter, void *stream) {
-    if (!p || !actions_host || !actions_dev || !rewards_host || !dones_host) return FE_EINVAL;
-    int rc = set_device(p->device);
+    if (!p || !s || !st || !actions_host || !actions_dev || !rewards_host || !dones_host) return FE_EINVAL;
+    int rc = check_common(p, s, st);
     if (rc) return rc;
+    if (!obs_dev || !rewards_dev || !dones_dev) return FE_EINVAL;
+    if ((rc = set_device(p->device))) return rc;
     cudaStream_t q = (cudaStream_t)stream;
-    const size_t n = (size_t)p->num_envs;
-    cudaError_t e = cudaMemcpyAsync(actions_dev, actions_host, n * p->num_assets * sizeof(float), cudaMemcpyHostToDevice, q);
-    if (e != cudaSuccess) return (int)e;
-    rc = fe_step(p, s, st, actions_dev, obs_dev, rewards_dev, dones_dev, stats_dev, step_counter, stream);
-    if (rc) return rc;
-    e = cudaMemcpyAsync(rewards_host, rewards_dev, n * (p->out_f64 ? 8 : 4), cudaMemcpyDeviceToHost, q);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaMemcpyAsync(dones_host, dones_dev, n * sizeof(int32_t), cudaMemcpyDeviceToHost, q);
-    if (e != cudaSuccess) return (int)e;
+    const int64_t n = p->num_envs;
+    const int A = p->num_assets;
+    const size_t osz = p->out_f64 ? 8 : 4;
+    static const int ov_chunks = env_override("FE_HOST_CHUNKS");
+    int chunks = ov_chunks > 0 ? ov_chunks : 4;
+    int64_t per = ((n + chunks - 1) / chunks + 1023) & ~(int64_t)1023;
+    if (per < 16384) per = 16384; // below this a chunk's kernel is shorter than the launch + copy set-up it would hide
+    chunks = (int)((n + per - 1) / per);
+    HostPipe *hp = nullptr;
+    if (chunks > 1) {
+        hp = host_pipe(p->device);
+        if (!hp) return (int)cudaGetLastError();
+        cudaError_t e = cudaEventRecord(hp->start, q);
+        if (e != cudaSuccess) return (int)e;
+    }
+    for (int c = 0; c < chunks; ++c) {
+        const int64_t off = (int64_t)c * per, cnt = off + per <= n ? per : n - off;
+        cudaStream_t cs = hp ? hp->s[c % kHostStreams] : q;
+        cudaError_t e;
+        if (hp && c < kHostStreams && (e = cudaStreamWaitEvent(cs, hp->start, 0)) != cudaSuccess) return (int)e;
+        e = cudaMemcpyAsync(actions_dev + off * A, actions_host + off * A, (size_t)cnt * A * sizeof(float),
+                            cudaMemcpyHostToDevice, cs);
+        if (e != cudaSuccess) return (int)e;
+        FeParams pc = *p;
+        pc.num_envs = cnt;
+        pc.env_id_base = p->env_id_base + off;
+        FeState sc = *st;
+        sc.seg += off; sc.ptr += off; sc.cash += off;
+        sc.long_sh += off * A; sc.short_sh += off * A; sc.margin += off * A;
+        if (sc.terminated) sc.terminated += off;
+        if (sc.ep_return) sc.ep_return += off;
+        if (sc.ep_len) sc.ep_len += off;
+        const size_t obs_off = (size_t)off * p->window * 5 * A * osz;
+        rc = fe_step(&pc, s, &sc, actions_dev + off * A, (char *)obs_dev + obs_off, (char *)rewards_dev + off * osz,
+                     dones_dev + off, stats_dev, step_counter, cs);
+        if (rc) return rc;
+        e = cudaMemcpyAsync((char *)rewards_host + off * osz, (char *)rewards_dev + off * osz, (size_t)cnt * osz,
+                            cudaMemcpyDeviceToHost, cs);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaMemcpyAsync(dones_host + off, dones_dev + off, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, cs);
+        if (e != cudaSuccess) return (int)e;
+    }
+    if (hp) { // the caller's stream continues only after every side stream has finished
+        for (int k = 0; k < kHostStreams && k < chunks; ++k) {
+            cudaError_t e = cudaEventRecord(hp->done[k], hp->s[k]);
+            if (e != cudaSuccess) return (int)e;
+            if ((e = cudaStreamWaitEvent(q, hp->done[k], 0)) != cudaSuccess) return (int)e;
+        }
+    }
     return (int)cudaStreamSynchronize(q);
 }
 

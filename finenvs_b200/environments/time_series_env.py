@@ -35,7 +35,7 @@ except Exception:  # pragma: no cover - gym is not installed in the target image
 
 _RESET_MODES = {"keep": _lib.RESET_KEEP, "last": _lib.RESET_LAST, "all": _lib.RESET_ALL}
 _VARIANTS = {"auto": _lib.VARIANT_AUTO, "tile": _lib.VARIANT_TILE, "direct": _lib.VARIANT_DIRECT,
-             "portfolio": _lib.VARIANT_PORTFOLIO}
+             "portfolio": _lib.VARIANT_PORTFOLIO, "pipe": _lib.VARIANT_PIPE}
 
 
 class TimeSeriesEnv(BaseObject):
@@ -79,7 +79,8 @@ class TimeSeriesEnv(BaseObject):
                       population (multi-GPU); draws are keyed by global id, so results do not
                       depend on the sharding.
         track_stats   accumulate episode count / return / length on the device (stats()).
-        variant       "auto" | "tile" | "direct" | "portfolio" kernel variant.
+        variant       "auto" | "pipe" | "tile" | "direct" | "portfolio" kernel variant (auto: pipe for populations
+                      of >= 18 944 envs, else tile; direct when the window does not fit in shared memory).
         flat_obs      return observations as (N, W*num_obs) — the 2-D input the ES agent's ParallelMLP needs
                       (parallel_mlp.py:98-103); same memory, only the shape differs.
         num_eval_envs reported in get_env_args() for the ES agent (evo_agent.py:53); the last
@@ -349,6 +350,10 @@ class TimeSeriesEnv(BaseObject):
         if self._stats is not None:
             self._stats.zero_()
         return self.reset()
+
+    def kernel_name(self) -> str:
+        """Which kernel step() launches for this env's shape (diagnostics)."""
+        return self._L.fe_step_kernel_name(self._pp).decode()
 
     def stats(self) -> Dict[str, torch.Tensor]:
         """Device-side episode statistics accumulated since the last clear (track_stats=True)."""

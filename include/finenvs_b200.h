@@ -37,9 +37,10 @@ extern "C" {
 #define FE_RESET_ALL 2   /* extension: every finished env redraws its segment */
 
 /* FeParams.variant */
-#define FE_VARIANT_AUTO 0   /* bulk-copy (TMA) tile kernel when the window fits in shared memory, else direct */
+#define FE_VARIANT_AUTO 0   /* pipe for large populations, else tile when the window fits in shared memory, else direct */
 #define FE_VARIANT_TILE 1   /* cp.async.bulk in -> smem interleave -> cp.async.bulk out */
 #define FE_VARIANT_DIRECT 2 /* warp-per-env global->global copy (any window) */
+#define FE_VARIANT_PIPE 4  /* persistent warp-specialised pipeline (bookkeeper / mover warps, multi-stage rings) */
 #define FE_VARIANT_PORTFOLIO 3 /* block-per-env, lane-per-asset kernel; always used when num_assets > 1 */
 
 typedef struct FeParams {
@@ -102,6 +103,13 @@ const char *fe_error_string(int code);
 /* Shared-memory bytes per env the tile variant needs for (window, out_f64), and the envs-per-block it
  * would pick (0 = does not fit, the direct variant is used). */
 int fe_tile_envs(int32_t window, int32_t out_f64, int32_t device);
+/* Envs per tile (<= 32, multiple of 4) the pipe variant would use for (window, out_f64) in its "cached"
+ * (stream_flavour = 0: series L2-resident, register prefetch) or "stream" (1: cp.async in-ring) flavour;
+ * 0 if the window does not fit (the tile / direct variants are used instead). */
+int fe_pipe_envs(int32_t window, int32_t out_f64, int32_t stream_flavour);
+
+/* Name of the kernel fe_step / fe_observe will launch for these parameters (diagnostics, bench.py). */
+const char *fe_step_kernel_name(const FeParams *p);
 
 /* generate_log_return_dataset (:179-194): logret[t,a,0] = 100*log(O_t/C_{t-1}) (row 0: O_0/O_0),
  * logret[t,a,1..3] = 100*log(H|L|C / O).  Either output may be NULL. */

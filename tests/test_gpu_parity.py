@@ -14,6 +14,12 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5  # north-star tolerance for fp32 cash / position / reward / observation values
 
 
+def _lib_mod():
+    from finenvs_b200 import _lib
+
+    return _lib
+
+
 def _env(series, **kw):
     from finenvs_b200.environments import TimeSeriesEnv
 
@@ -23,9 +29,12 @@ def _env(series, **kw):
 @pytest.mark.parametrize("name", golden_traces())
 @pytest.mark.parametrize("dtype,variant", [(torch.float32, "auto"), (torch.float64, "auto"), (torch.float32, "direct"),
                                            (torch.float64, "direct"), (torch.float32, "portfolio"),
-                                           (torch.float64, "portfolio")])
+                                           (torch.float64, "portfolio"), (torch.float32, "pipe"),
+                                           (torch.float64, "pipe")])
 def test_cuda_replays_reference_trace(name, dtype, variant):
     z = load_trace(name)
+    if variant == "pipe" and _lib_mod().lib().fe_pipe_envs(int(z["window"]), int(dtype == torch.float64), 0) == 0:
+        pytest.skip("window too large for the pipe variant's rings")
     series = stage_trace_series(z, dtype)
     N = len(z["seg_init"])
     env = _env(series, num_envs=N, evaluate=bool(z["evaluate"]), seed=int(z["seed"]), obs_dtype=dtype, variant=variant)
@@ -445,3 +454,49 @@ def test_flat_obs_and_es_env_args():
     assert ob.shape == (500, W * 5) and ob.dtype == torch.float32 and torch.equal(oa.view(500, -1), ob)
     o0 = b.reset_all()
     assert o0.shape == (500, W * 5) and int(b._ptr.abs().sum()) == 0 and float(b._cash.min()) == 10000.0
+
+
+@pytest.mark.parametrize("W,N,dtype", [(60, 1024, torch.float32), (60, 5003, torch.float32), (60, 4099, torch.float64),
+                                       (8, 70001, torch.float32), (128, 3000, torch.float32), (3, 999, torch.float32)])
+def test_pipe_variant_vs_oracle(W, N, dtype):
+    """The persistent warp-specialised pipeline: many tiles per block (N >> 148 * 32), ragged last tile, small and
+    larger windows (32/16/8-env tiles), both dtypes, resets with redraws — exact against the oracle."""
+    from oracle import oracle as orc
+    from finenvs_b200.data import loader
+
+    prices, seg_start, seg_len = _c1_series(W, days=80, bars=37, sigma=0.05, seed=W * 7 + N)
+    series = loader.stage_series(prices, seg_start, seg_len, W, "cuda:0", dtype, keep_logret64=True)
+    fs = orc.series_from_prices(prices, seg_start, seg_len, W, logret=series.logret64.cpu().numpy())
+    env = _env(series, num_envs=N, seed=4, random_reset="all", random_offset=True, obs_dtype=dtype, variant="pipe",
+               track_stats=True)
+    ref = orc.OracleEnv(fs, num_envs=N, seed=4, reset_mode=2, random_offset=True, out_f64=dtype == torch.float64)
+    n_done = _lockstep(env, ref, 60, np.random.default_rng(N), obs_every=4)
+    assert n_done > 0 and int(env.stats()["n_done"].item()) == n_done
+
+
+@pytest.mark.parametrize("N,A,dtype", [(70001, 1, torch.float32), (40000, 1, torch.float64), (9000, 1, torch.float32),
+                                       (33000, 3, torch.float32)])
+def test_step_host_pipeline_equals_device_step(N, A, dtype):
+    """fe_step_host cuts the envs into chunks on side streams (upload / kernel / download overlapped): same
+    results as the one-launch device-resident step, for ragged chunk counts, both dtypes, A > 1, with statistics."""
+    from finenvs_b200.data import loader
+
+    W = 12
+    if A == 1:
+        prices, seg_start, seg_len = _c1_series(W, days=50, bars=30, sigma=0.04, seed=N)
+    else:
+        prices, seg_start, seg_len = _portfolio_series(A, W, 50, 30, 0.04, N)
+    series = loader.stage_series(prices, seg_start, seg_len, W, "cuda:0", dtype)
+    kw = dict(num_envs=N, seed=21, random_reset="all", random_offset=True, obs_dtype=dtype, track_stats=True)
+    a_env, b_env = _env(series, **kw), _env(series, **kw)
+    g = torch.Generator().manual_seed(N)
+    for t in range(45):
+        a = (torch.rand((N, A), generator=g) * 2 - 1)
+        o1, r1, d1, _ = a_env.step(a.cuda())
+        o2, r2, d2, _ = b_env.step_host(a.pin_memory() if t % 2 else a)
+        assert r2.device.type == "cpu" and d2.device.type == "cpu"
+        assert torch.equal(o1, o2) and torch.equal(r1.cpu(), r2) and torch.equal(d1.cpu(), d2)
+        for k in ("_seg", "_ptr", "_cash", "_long", "_short", "_margin"):
+            assert torch.equal(getattr(a_env, k), getattr(b_env, k)), k
+    sa, sb = a_env.stats(), b_env.stats()
+    assert int(sa["n_done"]) == int(sb["n_done"]) > 0 and int(sa["sum_len"]) == int(sb["sum_len"])
