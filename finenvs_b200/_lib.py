@@ -80,6 +80,8 @@ _PROTOTYPES = {
                                C.c_void_p]),
     "fe_reset_all": (C.c_int, [C.POINTER(FeParams), C.POINTER(FeSeries), C.POINTER(FeState), C.c_uint64, C.c_int32,
                                C.c_void_p]),
+    "fe_returns_advantages": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                        C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fe_philox": (None, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint32)]),
 }
 

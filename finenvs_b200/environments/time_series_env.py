@@ -259,6 +259,9 @@ class TimeSeriesEnv(BaseObject):
         # a fresh tensor every call: the PPO buffer keeps references to past observations (buffer.py:44-56)
         shape = ((self.num_envs, self.num_intervals * self.num_obs) if self.flat_obs
                  else (self.num_envs, self.num_intervals, self.num_obs))
+        ring = getattr(self, "_obs_ring", None)
+        if ring is not None:  # a rollout buffer bound with Buffer.bind_env: write straight into its storage
+            return ring.next_obs_slot(shape, self.obs_dtype)
         return torch.empty(shape, dtype=self.obs_dtype, device=self._dev)
 
     def reset(self) -> torch.Tensor:

@@ -146,6 +146,16 @@ int fe_reset_all(const FeParams *p, const FeSeries *s, const FeState *st, uint64
  * lets callers reproduce / pre-compute draws.  kind: 0 step-time reset, 1 reset_all / constructor. */
 void fe_philox(uint64_t seed, uint64_t env_id, uint64_t step, uint32_t kind, uint32_t out[4]);
 
+/* ---- callers of the step --------------------------------------------------------------- */
+
+/* PPO rollout returns (finenvs/agents/PPO/buffer.py:80-100, compute_returns_and_advantages) over a TIME-MAJOR
+ * rollout: rewards (T,N) float or double (rewards_f64), dones (T,N) int32, values (T,N) float, last_values (N,)
+ * float -> returns (T,N) float, advantages (T,N) float.  returns[t] = rewards[t] + (1-dones[t])*gamma*returns[t+1]
+ * with the reference's dtype promotion ("PPO rollout storage"). */
+int fe_returns_advantages(const void *rewards_dev, int32_t rewards_f64, const int32_t *dones_dev, const float *values_dev,
+                          const float *last_values_dev, int64_t num_envs, int32_t num_steps, double gamma,
+                          float *returns_dev, float *advantages_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

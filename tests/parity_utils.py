@@ -65,7 +65,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
 def golden_traces():
-    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".npz") and f != "dummy_csv.npz")
+    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".npz") and f.startswith(("trace_", "kat_")))
 
 
 def load_trace(name: str):

@@ -6,7 +6,7 @@ for v in "$@"; do
   [[ $v =~ ^b([0-9]+)m([0-9]+)i([0-9]+)o([0-9]+)r([0-9]+)$ ]] || { echo "bad spec $v"; exit 1; }
   /usr/local/cuda/bin/nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC -shared \
     -I include -DFE_PIPE_BOOK=${BASH_REMATCH[1]} -DFE_PIPE_MOVE=${BASH_REMATCH[2]} -DFE_PIPE_SIN=${BASH_REMATCH[3]} \
-    -DFE_PIPE_SOUT=${BASH_REMATCH[4]} -DFE_PIPE_RPT=${BASH_REMATCH[5]} -o finenvs_b200/libfe_$v.so finenvs_b200/csrc/fe_step.cu &
+    -DFE_PIPE_SOUT=${BASH_REMATCH[4]} -DFE_PIPE_RPT=${BASH_REMATCH[5]} -o finenvs_b200/libfe_$v.so finenvs_b200/csrc/*.cu &
 done
 wait
 ls finenvs_b200/libfe_*.so
