@@ -60,6 +60,13 @@ class FeState(C.Structure):
     ]
 
 
+FE_ES_MAX_LAYERS = 4
+
+
+class FeEsNet(C.Structure):
+    _fields_ = [("num_layers", C.c_int32), ("dims", C.c_int32 * (FE_ES_MAX_LAYERS + 1))]
+
+
 # FeStats as a flat tensor: 4 x u64 then 2 x f64 = 48 bytes
 STATS_BYTES = 48
 
@@ -82,6 +89,21 @@ _PROTOTYPES = {
                                C.c_void_p]),
     "fe_returns_advantages": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                         C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fe_observe_lazy": (C.c_int, [C.POINTER(FeParams), C.POINTER(FeSeries), C.POINTER(FeState), C.c_void_p, C.c_void_p,
+                                  C.c_void_p]),
+    "fe_step_lazy": (C.c_int, [C.POINTER(FeParams), C.POINTER(FeSeries), C.POINTER(FeState), C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "fe_materialize": (C.c_int, [C.POINTER(FeParams), C.POINTER(FeSeries), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fe_es_params_padded": (C.c_int64, [C.POINTER(FeEsNet)]),
+    "fe_es_packed_index": (C.c_int64, [C.POINTER(FeEsNet), C.c_int32, C.c_int32, C.c_int32]),
+    "fe_es_perturb": (C.c_int, [C.POINTER(FeEsNet), C.c_uint64, C.c_uint64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "fe_es_forward": (C.c_int, [C.POINTER(FeEsNet), C.c_void_p, C.c_void_p, C.c_float, C.c_int64, C.c_int64, C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_uint64, C.c_uint64,
+                                C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
+    "fe_es_gradient_scratch": (C.c_int64, [C.POINTER(FeEsNet), C.c_int64]),
+    "fe_es_gradient": (C.c_int, [C.POINTER(FeEsNet), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fe_es_store": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_void_p,
+                              C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fe_philox": (None, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint32)]),
 }
 

@@ -1,0 +1,433 @@
+// fe_es.cu — the ES rollout path around the env step: the reference's ParallelMLP
+// (finenvs/agents/networks/parallel_mlp.py) and EvoAgent.store (finenvs/agents/ES/evo_agent.py:96-112) as
+// sm_100a kernels sized for millions of envs per GPU.
+//
+// The reference keeps one full perturbed copy of the network PER ENV (parallel_mlp.py:112-155: N x params f32,
+// 2.3 TB at 4 Mi envs with the default net) and multiplies through it with batched matmuls.  Here:
+//   * a mirrored PAIR (env p uses theta + sigma*eps_p, env p + N/2 uses theta - sigma*eps_p, :121-136) shares one
+//     stored perturbation, kept as fp16 in a layout the forward kernel streams with 16-byte loads
+//     (pairs x P_pad halves: 1.3 GB for 512 Ki envs x a 300-8-1 net, instead of 5 GB f32 per-env copies);
+//   * eps is a pure function of (seed, generation, GLOBAL pair id, parameter index) — Philox4x32-10 + Box-Muller,
+//     fe_es_perturb — so results do not depend on how pairs are sharded over GPUs;
+//   * fe_es_forward evaluates both envs of a pair in one warp: the shared theta sits in shared memory, each lane
+//     owns a strided slice of the layer's inputs, the four dot-product families (theta.x+, theta.x-, eps.x+,
+//     eps.x-) are FMA chains in registers, and a butterfly reduce-scatter leaves one output per lane pair.
+//     With LAZY observations (fe_step_lazy) the kernel gathers the env's window straight from the staged series:
+//     the (N, W*5) observation tensor — 53 % of the step kernel's HBM traffic — is never written or read;
+//   * fe_es_gradient is the fitness-weighted column sum of eps (parallel_mlp.py:176-218) in one pass over eps;
+//   * fe_es_store keeps the per-env running returns and appends finished episodes to a device list with no host
+//     synchronisation (evo_agent.py:96-112 does nonzero + cat + .item() per step).
+// Packed parameter layout (theta f32, eps fp16, gradient f32): per layer l with (in, out): ceil(out/8) chunks of
+// 8 outputs; chunk c holds rows j = 0..in (row `in` is the bias, its input is the constant 1), 8 values per row:
+//     index(l, j, o) = off[l] + ((o / 8) * (in + 1) + j) * 8 + (o % 8).
+#include "finenvs_b200.h"
+#include "fe_common.cuh"
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace {
+
+constexpr int kEsWarps = 8;
+constexpr int kEsThreads = kEsWarps * 32;
+constexpr uint64_t kEsKey = 0x9E3779B97F4A7C15ull; // separates the ES streams from the env's redraw streams
+constexpr unsigned kAll = 0xFFFFFFFFu;
+
+struct EsLayout {
+    int L;
+    int in[FE_ES_MAX_LAYERS], out[FE_ES_MAX_LAYERS];
+    int64_t off[FE_ES_MAX_LAYERS + 1]; // off[L] = P_pad
+    int max_dim;
+};
+
+bool make_layout(const FeEsNet *net, EsLayout &lay) {
+    if (!net || net->num_layers < 1 || net->num_layers > FE_ES_MAX_LAYERS) return false;
+    lay.L = net->num_layers;
+    lay.off[0] = 0;
+    lay.max_dim = 0;
+    for (int l = 0; l <= lay.L; ++l) {
+        if (net->dims[l] < 1) return false;
+        if (net->dims[l] > lay.max_dim) lay.max_dim = net->dims[l];
+    }
+    for (int l = 0; l < lay.L; ++l) {
+        lay.in[l] = net->dims[l];
+        lay.out[l] = net->dims[l + 1];
+        lay.off[l + 1] = lay.off[l] + (int64_t)((lay.out[l] + 7) / 8) * (lay.in[l] + 1) * 8;
+    }
+    return true;
+}
+
+// two standard normals from two 32-bit draws (Box-Muller on 24-bit uniforms, u1 in (0,1], u2 in [0,1))
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float &z0, float &z1) {
+    const float u1 = (float)((a >> 8) + 1u) * 5.9604644775390625e-8f;
+    const float u2 = (float)(b >> 8) * 5.9604644775390625e-8f;
+    const float r = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincospif(2.0f * u2, &sn, &cs);
+    z0 = r * cs;
+    z1 = r * sn;
+}
+
+// ------------------------------------------------------------------------------------------
+// perturbations (parallel_mlp.py:112-155): eps[pair, q] ~ N(0, 1); the network uses theta +- sigma * eps
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+fe_es_perturb_kernel(const int64_t total8, const int64_t num_pairs, const int64_t pair_id_base, const uint64_t seed,
+                     const uint64_t generation, __half *__restrict__ eps) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= num_pairs * total8) return;
+    const int64_t pair = idx / total8, q8 = idx - pair * total8;
+    float z[8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        uint32_t r[4];
+        philox4x32_10(seed ^ kEsKey, (uint64_t)(pair_id_base + pair), (generation << 32) | (uint64_t)(q8 * 2 + h), 1u, r);
+        box_muller(r[0], r[1], z[4 * h + 0], z[4 * h + 1]);
+        box_muller(r[2], r[3], z[4 * h + 2], z[4 * h + 3]);
+    }
+    __half2 h2[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h2[i] = __floats2half2_rn(z[2 * i], z[2 * i + 1]);
+    *reinterpret_cast<uint4 *>(eps + idx * 8) = *reinterpret_cast<const uint4 *>(h2);
+}
+
+__device__ __forceinline__ void halves8_to_floats(const uint4 v, float e[8]) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        __half2 h;
+        *reinterpret_cast<uint32_t *>(&h) = w[i];
+        const float2 f = __half22float2(h);
+        e[2 * i] = f.x;
+        e[2 * i + 1] = f.y;
+    }
+}
+
+// one level of the butterfly reduce-scatter: 2*kHalf live values -> kHalf (exchange with lane ^ 2*kHalf)
+template <int kHalf> __device__ __forceinline__ void butterfly_step(float (&v)[16], const int lane) {
+    const bool upper = (lane & (2 * kHalf)) != 0;
+#pragma unroll
+    for (int i = 0; i < kHalf; ++i) {
+        const float keep = upper ? v[i + kHalf] : v[i];
+        const float send = upper ? v[i] : v[i + kHalf];
+        v[i] = keep + __shfl_xor_sync(kAll, send, 2 * kHalf);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// forward (parallel_mlp.py:84-109): actions = tanh(... tanh(x W1' + b1') ...) with W' = W +- sigma * eps, per env
+// ------------------------------------------------------------------------------------------
+template <bool kLazy, bool kThetaSmem>
+__global__ void __launch_bounds__(kEsThreads)
+fe_es_forward_kernel(const EsLayout lay, const float *__restrict__ theta, const __half *__restrict__ eps, const float sigma,
+                     const int64_t num_pairs, const int64_t num_eval, const float *__restrict__ obs,
+                     const float *__restrict__ logret, const int64_t *__restrict__ row0, const float *__restrict__ posfeat,
+                     const int W, const float noise_std, const uint64_t seed, const uint64_t step,
+                     const int64_t env_id_base, float *__restrict__ actions) {
+    extern __shared__ __align__(16) float es_smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t P = lay.off[lay.L];
+    const int stride = (lay.max_dim + 1 + 3) & ~3; // one sign's activations (+ the constant-1 bias input)
+    float *th = es_smem;
+    float *bufA = es_smem + (kThetaSmem ? P : 0) + (size_t)warp * 4 * stride;
+    float *bufB = bufA + 2 * stride;
+    if (kThetaSmem) {
+        for (int64_t q = tid; q < P; q += kEsThreads) th[q] = theta[q];
+        __syncthreads();
+    }
+    const float *thbase = kThetaSmem ? th : theta;
+    const int I = lay.in[0], OL = lay.out[lay.L - 1];
+    const int64_t units = num_pairs + num_eval;
+    for (int64_t unit = (int64_t)blockIdx.x * kEsWarps + warp; unit < units; unit += (int64_t)gridDim.x * kEsWarps) {
+        const bool is_eval = unit >= num_pairs;
+        const int64_t e0 = is_eval ? 2 * num_pairs + (unit - num_pairs) : unit; // :121-136 positives first,
+        const int64_t e1 = is_eval ? e0 : unit + num_pairs;                      // negatives second, eval envs last
+        const float sg = is_eval ? 0.0f : sigma;
+        // ---- inputs of layer 0 into bufA: [0][.] = env e0, [1][.] = env e1
+        if (kLazy) {
+#pragma unroll
+            for (int sgn = 0; sgn < 2; ++sgn) {
+                const int64_t e = sgn ? e1 : e0;
+                const float4 *src = reinterpret_cast<const float4 *>(logret) + row0[e];
+                const float pfe = posfeat[e];
+                float *x = bufA + sgn * stride;
+                for (int r = lane; r < W; r += 32) {
+                    const float4 v = __ldg(src + r);
+                    x[r * 5 + 0] = v.x; x[r * 5 + 1] = v.y; x[r * 5 + 2] = v.z; x[r * 5 + 3] = v.w;
+                    x[r * 5 + 4] = pfe;
+                }
+            }
+        } else {
+            for (int j = lane; j < I; j += 32) {
+                bufA[j] = __ldg(obs + e0 * I + j);
+                bufA[stride + j] = __ldg(obs + e1 * I + j);
+            }
+        }
+        if (lane == 0) { bufA[I] = 1.0f; bufA[stride + I] = 1.0f; }
+        __syncwarp();
+        float *xin = bufA, *xout = bufB;
+        for (int l = 0; l < lay.L; ++l) {
+            const int in1 = lay.in[l] + 1, out = lay.out[l];
+            const float *thl = thbase + lay.off[l];
+            const __half *epl = eps + (is_eval ? 0 : unit * P) + lay.off[l];
+            for (int c = 0; c * 8 < out; ++c) {
+                float a0[8], a1[8], b0[8], b1[8];
+#pragma unroll
+                for (int o = 0; o < 8; ++o) { a0[o] = 0.0f; a1[o] = 0.0f; b0[o] = 0.0f; b1[o] = 0.0f; }
+#pragma unroll 2
+                for (int j = lane; j < in1; j += 32) {
+                    const size_t q = ((size_t)c * in1 + j) * 8;
+                    const float4 t03 = *reinterpret_cast<const float4 *>(thl + q);
+                    const float4 t47 = *reinterpret_cast<const float4 *>(thl + q + 4);
+                    const float t[8] = {t03.x, t03.y, t03.z, t03.w, t47.x, t47.y, t47.z, t47.w};
+                    float e[8];
+                    uint4 ev = make_uint4(0u, 0u, 0u, 0u);
+                    if (!is_eval) ev = __ldg(reinterpret_cast<const uint4 *>(epl + q));
+                    halves8_to_floats(ev, e);
+                    const float xp = xin[j], xm = xin[stride + j];
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) {
+                        a0[o] = fmaf(t[o], xp, a0[o]);
+                        a1[o] = fmaf(t[o], xm, a1[o]);
+                        b0[o] = fmaf(e[o], xp, b0[o]);
+                        b1[o] = fmaf(e[o], xm, b1[o]);
+                    }
+                }
+                float v[16];
+#pragma unroll
+                for (int o = 0; o < 8; ++o) {
+                    v[o] = fmaf(sg, b0[o], a0[o]);       // (theta + sigma eps) . x+
+                    v[8 + o] = fmaf(-sg, b1[o], a1[o]);  // (theta - sigma eps) . x-
+                }
+                // butterfly reduce-scatter: 16 partial sums x 32 lanes -> lanes 2m, 2m+1 hold the total of value m
+                butterfly_step<8>(v, lane);
+                butterfly_step<4>(v, lane);
+                butterfly_step<2>(v, lane);
+                butterfly_step<1>(v, lane);
+                v[0] += __shfl_xor_sync(kAll, v[0], 1);
+                const int m = lane >> 1, o = c * 8 + (m & 7);
+                if ((lane & 1) == 0 && o < out) xout[(m >> 3) * stride + o] = tanhf(v[0]);
+            }
+            if (lane == 0) { xout[out] = 1.0f; xout[stride + out] = 1.0f; }
+            __syncwarp();
+            float *tmp = xin; xin = xout; xout = tmp;
+        }
+        // ---- actions (+ exploration noise, parallel_mlp.py:104-109: none for the eval envs; with no eval envs the
+        //      reference's `action_noise[-0:, :] = 0` zeroes ALL of it)
+        for (int f = lane; f < 2 * OL; f += 32) {
+            const int sgn = f >= OL, o = f - sgn * OL;
+            if (sgn && is_eval) continue;
+            const int64_t e = sgn ? e1 : e0;
+            float a = xin[sgn * stride + o];
+            if (noise_std > 0.0f && !is_eval && num_eval > 0) {
+                uint32_t r[4]; // one Philox block = four normals: actions 4b .. 4b+3 of this (env, step)
+                philox4x32_10(seed ^ kEsKey, (uint64_t)(env_id_base + e), step | ((uint64_t)(o >> 2) << 48), 0u, r);
+                float z[4];
+                box_muller(r[0], r[1], z[0], z[1]);
+                box_muller(r[2], r[3], z[2], z[3]);
+                a = fmaf(noise_std, (o & 2) ? ((o & 1) ? z[3] : z[2]) : ((o & 1) ? z[1] : z[0]), a);
+            }
+            actions[e * OL + o] = a;
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// gradient (parallel_mlp.py:176-218): grad[q] = sum over pairs of w[pair] * eps[pair, q], w = f+ - f-.
+// Deterministic two-stage sum: slabs of pairs -> partial[slab, q]; then the slabs in order.
+// ------------------------------------------------------------------------------------------
+constexpr int kGradThreads = 128;
+constexpr int kGradSlab = 512; // pairs per block
+
+__global__ void __launch_bounds__(kGradThreads)
+fe_es_grad_partial_kernel(const int64_t total8, const int64_t num_pairs, const __half *__restrict__ eps,
+                          const float *__restrict__ w, float *__restrict__ partial) {
+    const int64_t q8 = (int64_t)blockIdx.x * kGradThreads + threadIdx.x;
+    if (q8 >= total8) return;
+    const int64_t p0 = (int64_t)blockIdx.y * kGradSlab;
+    const int64_t p1 = p0 + kGradSlab < num_pairs ? p0 + kGradSlab : num_pairs;
+    float acc[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = 0.0f;
+#pragma unroll 4
+    for (int64_t p = p0; p < p1; ++p) {
+        float e[8];
+        halves8_to_floats(__ldg(reinterpret_cast<const uint4 *>(eps + (p * total8 + q8) * 8)), e);
+        const float wp = __ldg(w + p);
+#pragma unroll
+        for (int o = 0; o < 8; ++o) acc[o] = fmaf(wp, e[o], acc[o]);
+    }
+    float4 *dst = reinterpret_cast<float4 *>(partial + ((int64_t)blockIdx.y * total8 + q8) * 8);
+    dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+}
+
+__global__ void __launch_bounds__(256)
+fe_es_grad_reduce_kernel(const int64_t total, const int64_t slabs, const float *__restrict__ partial, float *__restrict__ grad) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= total) return;
+    float s = 0.0f;
+    for (int64_t y = 0; y < slabs; ++y) s += partial[y * total + q];
+    grad[q] = s;
+}
+
+// ------------------------------------------------------------------------------------------
+// episode accounting (evo_agent.py:90-112): running return / step count per env, finished episodes appended to a
+// device list (key = step ordinal * total_envs + global env id, so sorting by key restores the reference's order)
+// ------------------------------------------------------------------------------------------
+template <typename RewT>
+__global__ void __launch_bounds__(256)
+fe_es_store_kernel(const RewT *__restrict__ rewards, const int32_t *__restrict__ dones, const int64_t N,
+                   const int64_t env_id_base, const int64_t total_envs, const uint64_t step_ordinal,
+                   float *__restrict__ cur_returns, float *__restrict__ cur_steps, const int64_t capacity,
+                   unsigned long long *__restrict__ counters, int64_t *__restrict__ fin_key, int64_t *__restrict__ fin_env,
+                   float *__restrict__ fin_ret) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int done = 0;
+    float ret = 0.0f, steps = 0.0f;
+    if (i < N) {
+        // :99 current_returns (f32) += rewards: computed in the promoted dtype, rounded once
+        if constexpr (sizeof(RewT) == 8) ret = __double2float_rn(__dadd_rn((double)cur_returns[i], rewards[i]));
+        else ret = __fadd_rn(cur_returns[i], rewards[i]);
+        steps = cur_steps[i] + 1.0f; // :93 current_timesteps += 1 (EvoAgent.step)
+        done = dones[i] != 0;
+        cur_returns[i] = done ? 0.0f : ret;   // :110-111
+        cur_steps[i] = done ? 0.0f : steps;
+    }
+    // one counter update per warp; slots inside the warp in lane (= env) order
+    const unsigned ballot = __ballot_sync(kAll, done);
+    if (ballot == 0) return;
+    float wsteps = done ? steps : 0.0f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wsteps += __shfl_xor_sync(kAll, wsteps, o);
+    unsigned long long base = 0;
+    if (lane == 0) {
+        base = atomicAdd(&counters[0], (unsigned long long)__popc(ballot));
+        atomicAdd(&counters[1], (unsigned long long)wsteps); // :103-104 total_timesteps
+    }
+    base = __shfl_sync(kAll, base, 0);
+    if (done) {
+        const int64_t slot = (int64_t)base + __popc(ballot & ((1u << lane) - 1u));
+        if (slot < capacity) {
+            fin_key[slot] = (int64_t)step_ordinal * total_envs + env_id_base + i;
+            fin_env[slot] = i;
+            fin_ret[slot] = ret;
+        }
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+int64_t fe_es_params_padded(const FeEsNet *net) {
+    EsLayout lay;
+    return make_layout(net, lay) ? lay.off[lay.L] : -1;
+}
+
+int64_t fe_es_packed_index(const FeEsNet *net, int32_t layer, int32_t input, int32_t output) {
+    EsLayout lay;
+    if (!make_layout(net, lay) || layer < 0 || layer >= lay.L) return -1;
+    if (input < 0 || input > lay.in[layer] || output < 0 || output >= lay.out[layer]) return -1;
+    return lay.off[layer] + ((int64_t)(output / 8) * (lay.in[layer] + 1) + input) * 8 + (output % 8);
+}
+
+int fe_es_perturb(const FeEsNet *net, uint64_t seed, uint64_t generation, int64_t pair_id_base, int64_t num_pairs,
+                  void *eps_dev, void *stream) {
+    EsLayout lay;
+    if (!make_layout(net, lay) || !eps_dev || num_pairs <= 0 || pair_id_base < 0 || generation >> 31) return FE_EINVAL;
+    if ((uintptr_t)eps_dev & 15) return FE_EALIGN;
+    const int64_t total8 = lay.off[lay.L] / 8, n = num_pairs * total8;
+    fe_es_perturb_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(total8, num_pairs, pair_id_base, seed,
+                                                                                        generation, (__half *)eps_dev);
+    return (int)cudaGetLastError();
+}
+
+int fe_es_forward(const FeEsNet *net, const float *theta_packed_dev, const void *eps_dev, float sigma, int64_t num_envs,
+                  int64_t num_eval_envs, const float *obs_dev, const void *logret_dev, const int64_t *obs_row0_dev,
+                  const float *obs_posfeat_dev, int32_t window, float action_noise_std, uint64_t seed,
+                  uint64_t step_counter, int64_t env_id_base, float *actions_dev, int32_t device, void *stream) {
+    EsLayout lay;
+    if (!make_layout(net, lay) || !theta_packed_dev || !actions_dev) return FE_EINVAL;
+    const int64_t train = num_envs - num_eval_envs;
+    if (num_envs <= 0 || num_eval_envs < 0 || train < 0 || (train & 1)) return FE_EINVAL; // mirrored sampling :24-27
+    if (train > 0 && !eps_dev) return FE_EINVAL;
+    const bool lazy = obs_dev == nullptr;
+    if (lazy) {
+        if (!logret_dev || !obs_row0_dev || !obs_posfeat_dev || window <= 0 || window * 5 != lay.in[0]) return FE_EINVAL;
+        if ((uintptr_t)logret_dev & 15) return FE_EALIGN;
+    }
+    if (((uintptr_t)eps_dev | (uintptr_t)theta_packed_dev) & 15) return FE_EALIGN;
+    cudaError_t e;
+    int cur = -1;
+    if ((e = cudaGetDevice(&cur)) != cudaSuccess) return (int)e;
+    if (cur != device && (e = cudaSetDevice(device)) != cudaSuccess) return (int)e;
+    static int num_sms[16] = {0};
+    const int dev = device & 15;
+    if (!num_sms[dev] && (e = cudaDeviceGetAttribute(&num_sms[dev], cudaDevAttrMultiProcessorCount, device)) != cudaSuccess)
+        return (int)e;
+    const int64_t P = lay.off[lay.L];
+    const int stride = (lay.max_dim + 1 + 3) & ~3;
+    const size_t act_bytes = (size_t)kEsWarps * 4 * stride * sizeof(float);
+    const bool theta_smem = act_bytes + (size_t)P * sizeof(float) <= 100 * 1024; // keep >= 2 blocks per SM
+    const size_t smem = act_bytes + (theta_smem ? (size_t)P * sizeof(float) : 0);
+    if (smem > 226 * 1024) return FE_ESMEM;
+    auto kern = lazy ? (theta_smem ? fe_es_forward_kernel<true, true> : fe_es_forward_kernel<true, false>)
+                     : (theta_smem ? fe_es_forward_kernel<false, true> : fe_es_forward_kernel<false, false>);
+    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
+    const int64_t units = train / 2 + num_eval_envs;
+    int per_sm = (int)((226 * 1024) / (smem + 1024));
+    if (per_sm > 8) per_sm = 8;
+    if (per_sm < 1) per_sm = 1;
+    int64_t blocks = (units + kEsWarps - 1) / kEsWarps;
+    if (blocks > (int64_t)num_sms[dev] * per_sm) blocks = (int64_t)num_sms[dev] * per_sm;
+    kern<<<(unsigned)blocks, kEsThreads, smem, (cudaStream_t)stream>>>(
+        lay, theta_packed_dev, (const __half *)eps_dev, sigma, train / 2, num_eval_envs, obs_dev, (const float *)logret_dev,
+        obs_row0_dev, obs_posfeat_dev, window, action_noise_std, seed, step_counter, env_id_base, actions_dev);
+    return (int)cudaGetLastError();
+}
+
+int64_t fe_es_gradient_scratch(const FeEsNet *net, int64_t num_pairs) {
+    EsLayout lay;
+    if (!make_layout(net, lay) || num_pairs <= 0) return -1;
+    return ((num_pairs + kGradSlab - 1) / kGradSlab) * lay.off[lay.L];
+}
+
+int fe_es_gradient(const FeEsNet *net, const void *eps_dev, const float *pair_weights_dev, int64_t num_pairs,
+                   float *scratch_dev, float *grad_packed_dev, void *stream) {
+    EsLayout lay;
+    if (!make_layout(net, lay) || !eps_dev || !pair_weights_dev || !scratch_dev || !grad_packed_dev || num_pairs <= 0)
+        return FE_EINVAL;
+    if (((uintptr_t)eps_dev | (uintptr_t)scratch_dev) & 15) return FE_EALIGN;
+    const int64_t total = lay.off[lay.L], total8 = total / 8, slabs = (num_pairs + kGradSlab - 1) / kGradSlab;
+    const dim3 grid((unsigned)((total8 + kGradThreads - 1) / kGradThreads), (unsigned)slabs);
+    fe_es_grad_partial_kernel<<<grid, kGradThreads, 0, (cudaStream_t)stream>>>(total8, num_pairs, (const __half *)eps_dev,
+                                                                               pair_weights_dev, scratch_dev);
+    fe_es_grad_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(total, slabs, scratch_dev,
+                                                                                               grad_packed_dev);
+    return (int)cudaGetLastError();
+}
+
+int fe_es_store(const void *rewards_dev, int32_t rewards_f64, const int32_t *dones_dev, int64_t num_envs,
+                int64_t env_id_base, int64_t total_envs, uint64_t step_ordinal, float *cur_returns_dev,
+                float *cur_steps_dev, int64_t capacity, unsigned long long *counters_dev, int64_t *fin_key_dev,
+                int64_t *fin_env_dev, float *fin_ret_dev, void *stream) {
+    if (!rewards_dev || !dones_dev || !cur_returns_dev || !cur_steps_dev || !counters_dev || !fin_key_dev || !fin_env_dev ||
+        !fin_ret_dev || num_envs <= 0 || capacity < 0)
+        return FE_EINVAL;
+    const unsigned blocks = (unsigned)((num_envs + 255) / 256);
+    if (rewards_f64)
+        fe_es_store_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+            (const double *)rewards_dev, dones_dev, num_envs, env_id_base, total_envs, step_ordinal, cur_returns_dev,
+            cur_steps_dev, capacity, counters_dev, fin_key_dev, fin_env_dev, fin_ret_dev);
+    else
+        fe_es_store_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+            (const float *)rewards_dev, dones_dev, num_envs, env_id_base, total_envs, step_ordinal, cur_returns_dev,
+            cur_steps_dev, capacity, counters_dev, fin_key_dev, fin_env_dev, fin_ret_dev);
+    return (int)cudaGetLastError();
+}
+
+} // extern "C"

@@ -18,6 +18,7 @@
 //
 // The C ABI is declared in include/finenvs_b200.h.
 #include "finenvs_b200.h"
+#include "fe_common.cuh"
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -61,31 +62,6 @@ Consts make_consts(const FeParams &p) {
     k.mmr1 = 1.0 + p.mmr;                          // :462
     k.SB = p.starting_balance;
     return k;
-}
-
-// ------------------------------------------------------------------------------------------
-// Philox4x32-10 keyed (seed) with counter (env id, step | kind<<63): the redraw RNG
-// (replaces torch.randint at :253 / :511; identical on host, see fe_philox)
-// ------------------------------------------------------------------------------------------
-__host__ __device__ __forceinline__ void philox4x32_10(uint64_t seed, uint64_t env_id, uint64_t step,
-                                                       uint32_t kind, uint32_t out[4]) {
-    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    uint32_t c0 = (uint32_t)env_id, c1 = (uint32_t)(env_id >> 32), c2 = (uint32_t)step,
-             c3 = ((uint32_t)(step >> 32) & 0x7FFFFFFFu) | (kind << 31);
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
-        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
-        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
-        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
-        c1 = (uint32_t)p1;
-        c3 = (uint32_t)p0;
-        c0 = n0;
-        c2 = n2;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
 __device__ __forceinline__ void draw_segment(const FeParams &p, const FeSeries &s, int64_t gid, uint64_t step,
@@ -672,6 +648,47 @@ fe_direct_kernel(const FeParams p, const FeSeries s, const FeState st, const Con
             const int j = f / 5, c = f - j * 5;
             dst[f] = c == 4 ? pfe : __ldg(src + j * 4 + c);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// lazy variant: the step WITHOUT materialising the observation.  An observation of this env is fully described by
+// (row0, position feature): obs[i, j, 0:4] = logret[row0[i] + j], obs[i, j, 4] = posfeat[i] (:437-445, :428-434).
+// Consumers that read the window straight from the staged series (the fused ES policy kernel, fe_es.cu) take the
+// 12-byte handle instead of the W x 20-byte tensor; fe_materialize turns a handle into the tensor.
+// ------------------------------------------------------------------------------------------
+template <typename OutT, bool kObserve>
+__global__ void __launch_bounds__(kThreads)
+fe_lazy_kernel(const FeParams p, const FeSeries s, const FeState st, const Consts k, const float *__restrict__ actions,
+               int64_t *__restrict__ row0_out, OutT *__restrict__ pf_out, OutT *__restrict__ rewards,
+               int32_t *__restrict__ dones, FeStats *stats, const uint64_t step) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const bool active = i < p.num_envs;
+    EnvResult r;
+    r.done = 0; r.newly_terminated = 0; r.fin_return = 0.0; r.fin_len = 0; r.row0 = 0; r.posfeat = 0.0;
+    if (active) {
+        if (kObserve) r = env_observe(p, s, st, k, i);
+        else r = env_step<OutT>(p, s, st, k, i, actions, rewards, dones, stats != nullptr, step);
+        row0_out[i] = r.row0;
+        pf_out[i] = (OutT)r.posfeat;
+    }
+    if (!kObserve) accumulate_stats(stats, r, active);
+}
+
+// handle -> tensor: warp per env, same element order as the direct variant
+template <typename OutT>
+__global__ void __launch_bounds__(kThreads)
+fe_materialize_kernel(const int64_t N, const int W, const OutT *__restrict__ logret, const int64_t *__restrict__ row0,
+                      const OutT *__restrict__ pf, OutT *__restrict__ obs) {
+    const int lane = threadIdx.x & 31;
+    const int64_t e = ((int64_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
+    if (e >= N) return;
+    const OutT *src = logret + row0[e] * 4;
+    OutT *dst = obs + (size_t)e * W * 5;
+    const OutT pfe = pf[e];
+    for (int f = lane; f < W * 5; f += 32) {
+        const int j = f / 5, c = f - j * 5;
+        dst[f] = c == 4 ? pfe : __ldg(src + j * 4 + c);
     }
 }
 
@@ -1268,6 +1285,60 @@ int fe_step(const FeParams *p, const FeSeries *s, const FeState *st, const float
                                               step_counter, (cudaStream_t)stream)
                       : launch<float, false>(*p, *s, *st, actions_dev, obs_dev, rewards_dev, dones_dev, stats_dev,
                                              step_counter, (cudaStream_t)stream);
+}
+
+int fe_observe_lazy(const FeParams *p, const FeSeries *s, const FeState *st, int64_t *obs_row0_dev, void *obs_posfeat_dev,
+                    void *stream) {
+    int rc = check_common(p, s, st);
+    if (rc) return rc;
+    if (!obs_row0_dev || !obs_posfeat_dev || p->num_assets != 1) return FE_EINVAL;
+    if ((rc = set_device(p->device))) return rc;
+    const Consts k = make_consts(*p);
+    const unsigned blocks = (unsigned)((p->num_envs + kThreads - 1) / kThreads);
+    if (p->out_f64)
+        fe_lazy_kernel<double, true><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(
+            *p, *s, *st, k, nullptr, obs_row0_dev, (double *)obs_posfeat_dev, nullptr, nullptr, nullptr, 0);
+    else
+        fe_lazy_kernel<float, true><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(
+            *p, *s, *st, k, nullptr, obs_row0_dev, (float *)obs_posfeat_dev, nullptr, nullptr, nullptr, 0);
+    return (int)cudaGetLastError();
+}
+
+int fe_step_lazy(const FeParams *p, const FeSeries *s, const FeState *st, const float *actions_dev, int64_t *obs_row0_dev,
+                 void *obs_posfeat_dev, void *rewards_dev, int32_t *dones_dev, FeStats *stats_dev, uint64_t step_counter,
+                 void *stream) {
+    int rc = check_common(p, s, st);
+    if (rc) return rc;
+    if (!actions_dev || !obs_row0_dev || !obs_posfeat_dev || !rewards_dev || !dones_dev || p->num_assets != 1) return FE_EINVAL;
+    if (stats_dev && !p->evaluate && (!st->ep_return || !st->ep_len)) return FE_EINVAL;
+    if ((rc = set_device(p->device))) return rc;
+    const Consts k = make_consts(*p);
+    const unsigned blocks = (unsigned)((p->num_envs + kThreads - 1) / kThreads);
+    if (p->out_f64)
+        fe_lazy_kernel<double, false><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(
+            *p, *s, *st, k, actions_dev, obs_row0_dev, (double *)obs_posfeat_dev, (double *)rewards_dev, dones_dev, stats_dev,
+            step_counter);
+    else
+        fe_lazy_kernel<float, false><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(
+            *p, *s, *st, k, actions_dev, obs_row0_dev, (float *)obs_posfeat_dev, (float *)rewards_dev, dones_dev, stats_dev,
+            step_counter);
+    return (int)cudaGetLastError();
+}
+
+int fe_materialize(const FeParams *p, const FeSeries *s, const int64_t *obs_row0_dev, const void *obs_posfeat_dev,
+                   void *obs_dev, void *stream) {
+    if (!p || !s || !s->logret || !obs_row0_dev || !obs_posfeat_dev || !obs_dev) return FE_EINVAL;
+    if (p->num_envs <= 0 || p->window <= 0 || p->num_assets != 1) return FE_EINVAL;
+    int rc = set_device(p->device);
+    if (rc) return rc;
+    const unsigned blocks = (unsigned)((p->num_envs * 32 + kThreads - 1) / kThreads);
+    if (p->out_f64)
+        fe_materialize_kernel<double><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(
+            p->num_envs, p->window, (const double *)s->logret, obs_row0_dev, (const double *)obs_posfeat_dev, (double *)obs_dev);
+    else
+        fe_materialize_kernel<float><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(
+            p->num_envs, p->window, (const float *)s->logret, obs_row0_dev, (const float *)obs_posfeat_dev, (float *)obs_dev);
+    return (int)cudaGetLastError();
 }
 
 // Host-buffer step, pipelined: the envs are cut into chunks (multiples of 1024 envs, so every chunk's slice of

@@ -38,6 +38,38 @@ _VARIANTS = {"auto": _lib.VARIANT_AUTO, "tile": _lib.VARIANT_TILE, "direct": _li
              "portfolio": _lib.VARIANT_PORTFOLIO, "pipe": _lib.VARIANT_PIPE}
 
 
+class LazyObs:
+    """An observation that has not been materialised: obs[i, j, 0:4] = logret[row0[i] + j], obs[i, j, 4] = posfeat[i]
+    (time_series_env.py:428-445).  12 bytes per env instead of W x 20; consumers that read the window straight from
+    the staged series (finenvs_b200.agents.networks.ParallelMLP.forward) never need the tensor."""
+
+    __slots__ = ("env", "row0", "posfeat")
+
+    def __init__(self, env: "TimeSeriesEnv", row0: torch.Tensor, posfeat: torch.Tensor):
+        self.env, self.row0, self.posfeat = env, row0, posfeat
+
+    @property
+    def logret(self) -> torch.Tensor:
+        return self.env.series.logret
+
+    @property
+    def window(self) -> int:
+        return self.env.num_intervals
+
+    @property
+    def shape(self):
+        e = self.env
+        return (e.num_envs, e.num_intervals * e.num_obs) if e.flat_obs else (e.num_envs, e.num_intervals, e.num_obs)
+
+    def materialize(self) -> torch.Tensor:
+        """The tensor step() would have returned for this observation."""
+        e = self.env
+        obs = torch.empty(self.shape, dtype=e.obs_dtype, device=e._dev)
+        _lib.check(e._L.fe_materialize(e._pp, e._ps, self.row0.data_ptr(), self.posfeat.data_ptr(), obs.data_ptr(), e._stream()),
+                   "fe_materialize")
+        return obs
+
+
 class TimeSeriesEnv(BaseObject):
     def __init__(
         self,
@@ -300,6 +332,36 @@ class TimeSeriesEnv(BaseObject):
             "fe_step",
         )
 
+    def _new_lazy(self) -> LazyObs:
+        if self.num_assets != 1:
+            raise NotImplementedError("lazy observations are implemented for single-asset envs")
+        return LazyObs(self, torch.empty(self.num_envs, dtype=torch.int64, device=self._dev),
+                       torch.empty(self.num_envs, dtype=self.obs_dtype, device=self._dev))
+
+    def reset_lazy(self) -> LazyObs:
+        """reset() returning a LazyObs handle instead of the tensor."""
+        lo = self._new_lazy()
+        _lib.check(self._L.fe_observe_lazy(self._pp, self._ps, self._pst, lo.row0.data_ptr(), lo.posfeat.data_ptr(),
+                                           self._stream()), "fe_observe_lazy")
+        return lo
+
+    def step_lazy(self, actions: torch.Tensor) -> Tuple[LazyObs, torch.Tensor, torch.Tensor, dict]:
+        """step() without materialising the observation: same state transition, rewards and dones; the observation
+        comes back as a LazyObs handle (`.materialize()` gives exactly the tensor step() returns)."""
+        actions = self._prepare_actions(actions)
+        lo = self._new_lazy()
+        rewards = torch.empty(self.num_envs, dtype=self.obs_dtype, device=self._dev)
+        dones = torch.empty(self.num_envs, dtype=torch.int32, device=self._dev)
+        self.step_count += 1
+        _lib.check(
+            self._L.fe_step_lazy(self._pp, self._ps, self._pst, actions.data_ptr(), lo.row0.data_ptr(), lo.posfeat.data_ptr(),
+                                 rewards.data_ptr(), dones.data_ptr(), self._stats.data_ptr() if self._stats is not None else None,
+                                 self.step_count, self._stream()),
+            "fe_step_lazy",
+        )
+        info_dict = self.record_evaluation_metrics() if self.evaluate else {}
+        return (lo, rewards, dones, info_dict)
+
     def step_host(self, actions_host: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, dict]:
         """step() for a host-resident policy, through fe_step_host: `actions_host` is a CPU tensor
         (pinned for full speed); rewards and dones come back as pinned CPU tensors, already complete when the
@@ -345,14 +407,14 @@ class TimeSeriesEnv(BaseObject):
         _lib.check(self._L.fe_reset_all(self._pp, self._ps, self._pst, self.step_count, int(redraw), self._stream()),
                    "fe_reset_all")
 
-    def reset_all(self, redraw: Optional[bool] = None) -> torch.Tensor:
+    def reset_all(self, redraw: Optional[bool] = None, lazy: bool = False):
         """Fresh episode for every env (the reset the ES loop expects, cf. isaac_gym_env.py:55-58)."""
         if redraw is None:
             redraw = self.random_reset == "all"
         self._launch_reset_all(redraw)
         if self._stats is not None:
             self._stats.zero_()
-        return self.reset()
+        return self.reset_lazy() if lazy else self.reset()
 
     def kernel_name(self) -> str:
         """Which kernel step() launches for this env's shape (diagnostics)."""

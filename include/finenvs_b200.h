@@ -130,6 +130,18 @@ int fe_observe(const FeParams *p, const FeSeries *s, const FeState *st, void *ob
 int fe_step(const FeParams *p, const FeSeries *s, const FeState *st, const float *actions_dev, void *obs_dev,
             void *rewards_dev, int32_t *dones_dev, FeStats *stats_dev, uint64_t step_counter, void *stream);
 
+/* Lazy observations (extension): an observation is fully described by the 12-byte handle (row0, posfeat):
+ * obs[i,j,0:4] = logret[row0[i]+j], obs[i,j,4] = posfeat[i] (:428-445).  fe_step_lazy / fe_observe_lazy are fe_step /
+ * fe_observe writing the handle instead of the (N,W,5) tensor (single-asset envs); fe_materialize builds the tensor
+ * from a handle (identical to what fe_step would have written).  Used by the fused ES policy (fe_es_forward). */
+int fe_observe_lazy(const FeParams *p, const FeSeries *s, const FeState *st, int64_t *obs_row0_dev, void *obs_posfeat_dev,
+                    void *stream);
+int fe_step_lazy(const FeParams *p, const FeSeries *s, const FeState *st, const float *actions_dev, int64_t *obs_row0_dev,
+                 void *obs_posfeat_dev, void *rewards_dev, int32_t *dones_dev, FeStats *stats_dev, uint64_t step_counter,
+                 void *stream);
+int fe_materialize(const FeParams *p, const FeSeries *s, const int64_t *obs_row0_dev, const void *obs_posfeat_dev,
+                   void *obs_dev, void *stream);
+
 /* Same step driven from HOST buffers (the call a non-torch embedder makes): copies actions host->device,
  * runs fe_step, copies rewards and dones device->host and waits for them.  The observation stays in HBM
  * (obs_dev) for the policy.  actions_host/rewards_host/dones_host should be pinned for full speed. */
@@ -155,6 +167,51 @@ void fe_philox(uint64_t seed, uint64_t env_id, uint64_t step, uint32_t kind, uin
 int fe_returns_advantages(const void *rewards_dev, int32_t rewards_f64, const int32_t *dones_dev, const float *values_dev,
                           const float *last_values_dev, int64_t num_envs, int32_t num_steps, double gamma,
                           float *returns_dev, float *advantages_dev, void *stream);
+
+/* ---- ES rollout path (finenvs/agents/networks/parallel_mlp.py, finenvs/agents/ES/evo_agent.py) -------------
+ * Population layout of the reference (parallel_mlp.py:121-136): envs [0, T/2) use theta + sigma*eps[p], envs
+ * [T/2, T) use theta - sigma*eps[p - T/2] (T = num_envs - num_eval_envs, even), the last num_eval_envs envs use
+ * theta.  Perturbations are stored per PAIR as fp16 in the packed layout
+ *     index(layer l, input j (j == in_l: bias), output o) = off[l] + ((o/8)*(in_l+1) + j)*8 + o%8,
+ * off[l+1] = off[l] + ceil(out_l/8)*(in_l+1)*8; theta and the gradient use the same layout in f32. */
+#define FE_ES_MAX_LAYERS 4
+typedef struct FeEsNet {
+    int32_t num_layers;                 /* weight layers: len(shape) - 1 (parallel_mlp.py:46-50) */
+    int32_t dims[FE_ES_MAX_LAYERS + 1]; /* shape: (num_observations, *hidden_dims, num_actions); tanh after every layer */
+} FeEsNet;
+
+/* P_pad: packed values per network; index of one parameter in the packed layout (-1: invalid). */
+int64_t fe_es_params_padded(const FeEsNet *net);
+int64_t fe_es_packed_index(const FeEsNet *net, int32_t layer, int32_t input, int32_t output);
+
+/* perturb_parameters (:112-155): eps[pair, q] ~ N(0,1) as a pure function of (seed, generation, pair_id_base + pair,
+ * q): Philox4x32-10 + Box-Muller.  eps_dev: (num_pairs, P_pad) fp16, 16-byte aligned.  generation < 2^31. */
+int fe_es_perturb(const FeEsNet *net, uint64_t seed, uint64_t generation, int64_t pair_id_base, int64_t num_pairs,
+                  void *eps_dev, void *stream);
+
+/* forward (:84-109) for every env: actions (N, num_actions) = MLP(theta +- sigma*eps)(obs) [+ N(0, action_noise_std)
+ * exploration noise, reference semantics: none for eval envs, none at all when num_eval_envs == 0].
+ * Observations: dense obs_dev (N, dims[0]) f32, or — obs_dev == NULL — lazy handles (obs_row0_dev, obs_posfeat_dev)
+ * from fe_step_lazy plus the staged log-return table logret_dev (T,4) f32 and window (dims[0] == window*5). */
+int fe_es_forward(const FeEsNet *net, const float *theta_packed_dev, const void *eps_dev, float sigma, int64_t num_envs,
+                  int64_t num_eval_envs, const float *obs_dev, const void *logret_dev, const int64_t *obs_row0_dev,
+                  const float *obs_posfeat_dev, int32_t window, float action_noise_std, uint64_t seed,
+                  uint64_t step_counter, int64_t env_id_base, float *actions_dev, int32_t device, void *stream);
+
+/* update_parameters' reduction (:176-218): grad_packed[q] = sum_p pair_weights[p] * eps[p, q] (pair_weights =
+ * fitness(+) - fitness(-)); deterministic.  scratch_dev: fe_es_gradient_scratch(net, num_pairs) floats. */
+int64_t fe_es_gradient_scratch(const FeEsNet *net, int64_t num_pairs);
+int fe_es_gradient(const FeEsNet *net, const void *eps_dev, const float *pair_weights_dev, int64_t num_pairs,
+                   float *scratch_dev, float *grad_packed_dev, void *stream);
+
+/* EvoAgent.step/.store accounting (evo_agent.py:90-112) without host synchronisation: cur_steps += 1,
+ * cur_returns += rewards; every done env appends (key, env, return) to the finished list (capacity entries; overflow
+ * is counted, not written), adds its step count to counters[1], and is zeroed.  counters[0] = finished episodes.
+ * key = step_ordinal * total_envs + env_id_base + env: sorting by key gives the reference's list order. */
+int fe_es_store(const void *rewards_dev, int32_t rewards_f64, const int32_t *dones_dev, int64_t num_envs,
+                int64_t env_id_base, int64_t total_envs, uint64_t step_ordinal, float *cur_returns_dev,
+                float *cur_steps_dev, int64_t capacity, unsigned long long *counters_dev, int64_t *fin_key_dev,
+                int64_t *fin_env_dev, float *fin_ret_dev, void *stream);
 
 #ifdef __cplusplus
 }
