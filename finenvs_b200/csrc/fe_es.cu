@@ -26,6 +26,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -235,6 +236,256 @@ fe_es_forward_kernel(const EsLayout lay, const float *__restrict__ theta, const 
 }
 
 // ------------------------------------------------------------------------------------------
+// forward, fast path: first layer 5*R inputs (R <= 64 window rows x 5 features) -> <= 8 outputs — the shape of the ES
+// population rollout on the trading env (BASELINE config 5: 300-8-1).  ncu on the generic kernel above
+// (profiles/r01_es_forward_generic_ncu.txt): 1.08 ms per 512 Ki envs, 1.65 TB/s, stalled on its own eps loads
+// (long scoreboard 10.6 of 12.7 stall cycles per issue, <= 1 KB in flight per warp).  Here
+//   * every warp owns a ring of kFastStages shared-memory stages; a unit's perturbation (P_pad fp16, contiguous) and
+//     its two observation windows arrive by 1-D bulk async copies (cp.async.bulk, UBLKCP) issued kFastStages-1 units
+//     ahead and completing on the stage's mbarrier: ~14 KB in flight per warp, no register staging;
+//   * lane r owns window rows r and r+32, i.e. inputs 5r..5r+4: the first layer's theta rows of a lane never change,
+//     so they live in registers for the whole kernel (80 floats) — shared memory only feeds eps and x;
+//   * the lazy window (W x 16 B straight from the staged series) is consumed as it lies: the 4->5 interleave with the
+//     position feature never happens anywhere.
+// The remaining (tiny) layers read theta from shared memory and eps from the stage.  Dense observations take the
+// same path (their rows are 5 consecutive floats), with the same FMA order, so lazy == dense bit for bit.
+// ------------------------------------------------------------------------------------------
+#ifndef FE_ES_FAST_WARPS
+#define FE_ES_FAST_WARPS 12
+#endif
+#ifndef FE_ES_FAST_STAGES
+#define FE_ES_FAST_STAGES 2
+#endif
+constexpr int kFastWarps = FE_ES_FAST_WARPS;
+constexpr int kFastThreads = kFastWarps * 32;
+constexpr int kFastStages = FE_ES_FAST_STAGES;
+
+struct FastShape {
+    int rows;        // R: window rows (in[0] == 5 * R)
+    int x_bytes;     // one env's layer-0 inputs as staged: lazy R*16, dense R*20
+    int eps_bytes;   // P_pad * 2
+    int stage_bytes; // eps + 2 x + pf pair, rounded to 128
+    int act_stride;  // floats per sign in the activation buffers of layers >= 1
+    int theta_bytes; // P_pad * 4 rounded to 128
+};
+__host__ __device__ inline size_t fast_smem_bytes(const FastShape &f) {
+    return 256 + (size_t)f.theta_bytes + (size_t)kFastWarps * ((size_t)kFastStages * f.stage_bytes + (size_t)4 * f.act_stride * 4);
+}
+
+template <bool kLazy>
+__global__ void __launch_bounds__(kFastThreads, 1)
+fe_es_forward_fast_kernel(const EsLayout lay, const FastShape fs, const float *__restrict__ theta,
+                          const __half *__restrict__ eps, const float sigma, const int64_t num_pairs, const int64_t num_eval,
+                          const float *__restrict__ obs, const float *__restrict__ logret, const int64_t *__restrict__ row0,
+                          const float *__restrict__ posfeat, const float noise_std, const uint64_t seed, const uint64_t step,
+                          const int64_t env_id_base, float *__restrict__ actions) {
+    extern __shared__ __align__(128) unsigned char fsm[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t P = lay.off[lay.L];
+    const int R = fs.rows, I = lay.in[0], out0 = lay.out[0], OL = lay.out[lay.L - 1];
+    float *th = reinterpret_cast<float *>(fsm + 256);
+    unsigned char *ring = fsm + 256 + fs.theta_bytes + (size_t)warp * kFastStages * fs.stage_bytes;
+    const int stride = fs.act_stride;
+    float *bufA = reinterpret_cast<float *>(fsm + 256 + fs.theta_bytes + (size_t)kFastWarps * kFastStages * fs.stage_bytes) +
+                  (size_t)warp * 4 * stride;
+    float *bufB = bufA + 2 * stride;
+    const uint32_t bar0 = smem_u32(fsm) + (uint32_t)warp * kFastStages * 8u;
+    for (int64_t q = tid; q < P; q += kFastThreads) th[q] = theta[q];
+    if (lane == 0)
+        for (int s = 0; s < kFastStages; ++s) mbar_init(bar0 + 8u * s, 1);
+    mbar_fence_init();
+    __syncthreads();
+
+    // lane-stationary first-layer theta: rows lane and lane + 32, five inputs each, eight outputs (packed index j*8 + o)
+    float t0[2][5][8];
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl) {
+        const int r = lane + 32 * sl;
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+#pragma unroll
+            for (int o = 0; o < 8; ++o) t0[sl][i][o] = r < R ? th[(size_t)(5 * r + i) * 8 + o] : 0.0f;
+    }
+
+    const int64_t units = num_pairs + num_eval;
+    const int64_t gw = (int64_t)blockIdx.x * kFastWarps + warp, nw = (int64_t)gridDim.x * kFastWarps;
+    const int64_t nloc = gw < units ? (units - gw + nw - 1) / nw : 0;
+    auto env_of = [&](int64_t u, int sgn) -> int64_t { // :121-136 positives first, negatives second, eval envs last
+        if (u >= num_pairs) return 2 * num_pairs + (u - num_pairs);
+        return sgn ? u + num_pairs : u;
+    };
+    // registers of lanes 0/1 describing the NEXT unit to issue (loaded one iteration early: no stall on row0)
+    int64_t n_src = 0;
+    float n_pf = 0.0f;
+    auto preload = [&](int64_t k) {
+        if (k < nloc && lane < 2) {
+            const int64_t e = env_of(gw + k * nw, lane);
+            if (kLazy) { n_src = __ldg(row0 + e); n_pf = __ldg(posfeat + e); }
+            else n_src = e;
+        }
+    };
+    auto issue = [&](int64_t k) {
+        if (k >= nloc) return;
+        const int64_t u = gw + k * nw;
+        const bool is_eval = u >= num_pairs;
+        unsigned char *stage = ring + (size_t)(k % kFastStages) * fs.stage_bytes;
+        const uint32_t bar = bar0 + 8u * (uint32_t)(k % kFastStages);
+        if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)((is_eval ? 0 : fs.eps_bytes) + 2 * fs.x_bytes));
+        __syncwarp();
+        if (lane == 0 && !is_eval) bulk_load(smem_u32(stage), eps + u * P, (uint32_t)fs.eps_bytes, bar);
+        if (lane < 2) {
+            const void *src = kLazy ? (const void *)(reinterpret_cast<const float4 *>(logret) + n_src)
+                                    : (const void *)(obs + n_src * I);
+            bulk_load(smem_u32(stage + fs.eps_bytes + lane * fs.x_bytes), src, (uint32_t)fs.x_bytes, bar);
+            if (kLazy) reinterpret_cast<float *>(stage + fs.eps_bytes + 2 * fs.x_bytes)[lane] = n_pf;
+        }
+    };
+    for (int64_t k = 0; k < kFastStages - 1; ++k) { preload(k); issue(k); }
+    preload(kFastStages - 1);
+
+    for (int64_t k = 0; k < nloc; ++k) {
+        issue(k + kFastStages - 1); // into the stage consumed in iteration k - 1
+        preload(k + kFastStages);
+        const int64_t unit = gw + k * nw;
+        const bool is_eval = unit >= num_pairs;
+        const int64_t e0 = env_of(unit, 0), e1 = env_of(unit, 1);
+        const float sg = is_eval ? 0.0f : sigma;
+        const unsigned char *stage = ring + (size_t)(k % kFastStages) * fs.stage_bytes;
+        mbar_wait(bar0 + 8u * (uint32_t)(k % kFastStages), (uint32_t)((k / kFastStages) & 1));
+        __syncwarp();
+        const unsigned char *xs = stage + fs.eps_bytes;
+        // ---- layer 0
+        float a0[8], a1[8], b0[8], b1[8];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) { a0[o] = 0.0f; a1[o] = 0.0f; b0[o] = 0.0f; b1[o] = 0.0f; }
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+            const int r = lane + 32 * sl;
+            if (r < R) {
+                float xp[5], xm[5];
+                if (kLazy) {
+                    const float4 p4 = *reinterpret_cast<const float4 *>(xs + (size_t)r * 16);
+                    const float4 m4 = *reinterpret_cast<const float4 *>(xs + fs.x_bytes + (size_t)r * 16);
+                    const float2 pf = *reinterpret_cast<const float2 *>(xs + 2 * fs.x_bytes);
+                    xp[0] = p4.x; xp[1] = p4.y; xp[2] = p4.z; xp[3] = p4.w; xp[4] = pf.x;
+                    xm[0] = m4.x; xm[1] = m4.y; xm[2] = m4.z; xm[3] = m4.w; xm[4] = pf.y;
+                } else {
+                    const float *pp = reinterpret_cast<const float *>(xs) + 5 * r;
+                    const float *pm = reinterpret_cast<const float *>(xs + fs.x_bytes) + 5 * r;
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) { xp[i] = pp[i]; xm[i] = pm[i]; }
+                }
+#pragma unroll
+                for (int i = 0; i < 5; ++i) {
+                    float e[8];
+                    uint4 ev = make_uint4(0u, 0u, 0u, 0u);
+                    if (!is_eval) ev = *reinterpret_cast<const uint4 *>(stage + (size_t)(5 * r + i) * 16);
+                    halves8_to_floats(ev, e);
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) {
+                        a0[o] = fmaf(t0[sl][i][o], xp[i], a0[o]);
+                        a1[o] = fmaf(t0[sl][i][o], xm[i], a1[o]);
+                        b0[o] = fmaf(e[o], xp[i], b0[o]);
+                        b1[o] = fmaf(e[o], xm[i], b1[o]);
+                    }
+                }
+            }
+        }
+        if (lane == 0) { // bias row (input == 1)
+            float e[8];
+            uint4 ev = make_uint4(0u, 0u, 0u, 0u);
+            if (!is_eval) ev = *reinterpret_cast<const uint4 *>(stage + (size_t)I * 16);
+            halves8_to_floats(ev, e);
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+                const float t = th[(size_t)I * 8 + o];
+                a0[o] += t; a1[o] += t; b0[o] += e[o]; b1[o] += e[o];
+            }
+        }
+        float v[16];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+            v[o] = fmaf(sg, b0[o], a0[o]);       // (theta + sigma eps) . x+
+            v[8 + o] = fmaf(-sg, b1[o], a1[o]);  // (theta - sigma eps) . x-
+        }
+        butterfly_step<8>(v, lane);
+        butterfly_step<4>(v, lane);
+        butterfly_step<2>(v, lane);
+        butterfly_step<1>(v, lane);
+        v[0] += __shfl_xor_sync(kAll, v[0], 1);
+        {
+            const int m = lane >> 1, o = m & 7;
+            if ((lane & 1) == 0 && o < out0) bufA[(m >> 3) * stride + o] = tanhf(v[0]);
+            if (lane == 0) { bufA[out0] = 1.0f; bufA[stride + out0] = 1.0f; }
+        }
+        __syncwarp();
+        // ---- layers 1 .. L-1: theta from shared memory, eps from the stage
+        float *xin = bufA, *xout = bufB;
+        for (int l = 1; l < lay.L; ++l) {
+            const int in1 = lay.in[l] + 1, out = lay.out[l];
+            const float *thl = th + lay.off[l];
+            const unsigned char *epl = stage + (size_t)lay.off[l] * 2;
+            for (int c = 0; c * 8 < out; ++c) {
+                float c0[8], c1[8], d0[8], d1[8];
+#pragma unroll
+                for (int o = 0; o < 8; ++o) { c0[o] = 0.0f; c1[o] = 0.0f; d0[o] = 0.0f; d1[o] = 0.0f; }
+                for (int j = lane; j < in1; j += 32) {
+                    const size_t q = ((size_t)c * in1 + j) * 8;
+                    const float4 t03 = *reinterpret_cast<const float4 *>(thl + q);
+                    const float4 t47 = *reinterpret_cast<const float4 *>(thl + q + 4);
+                    const float t[8] = {t03.x, t03.y, t03.z, t03.w, t47.x, t47.y, t47.z, t47.w};
+                    float e[8];
+                    uint4 ev = make_uint4(0u, 0u, 0u, 0u);
+                    if (!is_eval) ev = *reinterpret_cast<const uint4 *>(epl + q * 2);
+                    halves8_to_floats(ev, e);
+                    const float xp = xin[j], xm = xin[stride + j];
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) {
+                        c0[o] = fmaf(t[o], xp, c0[o]);
+                        c1[o] = fmaf(t[o], xm, c1[o]);
+                        d0[o] = fmaf(e[o], xp, d0[o]);
+                        d1[o] = fmaf(e[o], xm, d1[o]);
+                    }
+                }
+                float w[16];
+#pragma unroll
+                for (int o = 0; o < 8; ++o) {
+                    w[o] = fmaf(sg, d0[o], c0[o]);
+                    w[8 + o] = fmaf(-sg, d1[o], c1[o]);
+                }
+                butterfly_step<8>(w, lane);
+                butterfly_step<4>(w, lane);
+                butterfly_step<2>(w, lane);
+                butterfly_step<1>(w, lane);
+                w[0] += __shfl_xor_sync(kAll, w[0], 1);
+                const int m = lane >> 1, o = c * 8 + (m & 7);
+                if ((lane & 1) == 0 && o < out) xout[(m >> 3) * stride + o] = tanhf(w[0]);
+            }
+            if (lane == 0) { xout[out] = 1.0f; xout[stride + out] = 1.0f; }
+            __syncwarp();
+            float *tmp = xin; xin = xout; xout = tmp;
+        }
+        // ---- actions (+ exploration noise; same semantics and streams as the generic kernel)
+        for (int f = lane; f < 2 * OL; f += 32) {
+            const int sgn = f >= OL, o = f - sgn * OL;
+            if (sgn && is_eval) continue;
+            const int64_t e = sgn ? e1 : e0;
+            float a = xin[sgn * stride + o];
+            if (noise_std > 0.0f && !is_eval && num_eval > 0) {
+                uint32_t r[4];
+                philox4x32_10(seed ^ kEsKey, (uint64_t)(env_id_base + e), step | ((uint64_t)(o >> 2) << 48), 0u, r);
+                float z[4];
+                box_muller(r[0], r[1], z[0], z[1]);
+                box_muller(r[2], r[3], z[2], z[3]);
+                a = fmaf(noise_std, (o & 2) ? ((o & 1) ? z[3] : z[2]) : ((o & 1) ? z[1] : z[0]), a);
+            }
+            actions[e * OL + o] = a;
+        }
+        __syncwarp(); // every lane is done with this stage and the activation buffers
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // gradient (parallel_mlp.py:176-218): grad[q] = sum over pairs of w[pair] * eps[pair, q], w = f+ - f-.
 // Deterministic two-stage sum: slabs of pairs -> partial[slab, q]; then the slabs in order.
 // ------------------------------------------------------------------------------------------
@@ -370,6 +621,33 @@ int fe_es_forward(const FeEsNet *net, const float *theta_packed_dev, const void 
     if (!num_sms[dev] && (e = cudaDeviceGetAttribute(&num_sms[dev], cudaDevAttrMultiProcessorCount, device)) != cudaSuccess)
         return (int)e;
     const int64_t P = lay.off[lay.L];
+    // ---- fast path: 5R -> <= 8 first layer (R <= 64), inputs 16-byte granular, ring fits in shared memory
+    static const bool no_fast = getenv("FE_ES_NO_FAST") != nullptr; // A/B runs and the generic kernel's tests
+    if (!no_fast && lay.out[0] <= 8 && lay.in[0] % 5 == 0 && lay.in[0] / 5 <= 64 &&
+        (lazy || (lay.in[0] % 4 == 0 && ((uintptr_t)obs_dev & 15) == 0))) {
+        FastShape f;
+        f.rows = lay.in[0] / 5;
+        f.x_bytes = lazy ? f.rows * 16 : f.rows * 20;
+        f.eps_bytes = (int)(P * 2);
+        f.stage_bytes = (f.eps_bytes + 2 * f.x_bytes + 16 + 127) & ~127;
+        int md = 1;
+        for (int l = 1; l <= lay.L; ++l) md = lay.out[l - 1] > md ? lay.out[l - 1] : md;
+        f.act_stride = (md + 1 + 3) & ~3;
+        f.theta_bytes = (int)((P * 4 + 127) & ~(int64_t)127);
+        const size_t smem = fast_smem_bytes(f);
+        if (smem <= 226 * 1024) {
+            auto kern = lazy ? fe_es_forward_fast_kernel<true> : fe_es_forward_fast_kernel<false>;
+            if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
+            const int64_t units = train / 2 + num_eval_envs;
+            int64_t blocks = (units + kFastWarps - 1) / kFastWarps;
+            if (blocks > num_sms[dev]) blocks = num_sms[dev];
+            kern<<<(unsigned)blocks, kFastThreads, smem, (cudaStream_t)stream>>>(
+                lay, f, theta_packed_dev, (const __half *)eps_dev, sigma, train / 2, num_eval_envs, obs_dev,
+                (const float *)logret_dev, obs_row0_dev, obs_posfeat_dev, action_noise_std, seed, step_counter, env_id_base,
+                actions_dev);
+            return (int)cudaGetLastError();
+        }
+    }
     const int stride = (lay.max_dim + 1 + 3) & ~3;
     const size_t act_bytes = (size_t)kEsWarps * 4 * stride * sizeof(float);
     const bool theta_smem = act_bytes + (size_t)P * sizeof(float) <= 100 * 1024; // keep >= 2 blocks per SM

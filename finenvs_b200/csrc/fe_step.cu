@@ -270,8 +270,9 @@ template <typename OutT, bool kObserve>
 __global__ void __launch_bounds__(kThreads)
 fe_tile_kernel(const FeParams p, const FeSeries s, const FeState st, const Consts k, const float *__restrict__ actions,
                OutT *__restrict__ obs, OutT *__restrict__ rewards, int32_t *__restrict__ dones, FeStats *stats,
-               const uint64_t step, const int E) {
+               const uint64_t step_arg, const uint64_t *__restrict__ step_dev, const int E) {
     extern __shared__ __align__(128) unsigned char smem[];
+    const uint64_t step = step_dev ? *step_dev : step_arg;
     const int W = p.window;
     const int tid = threadIdx.x;
     const int64_t env0 = (int64_t)blockIdx.x * E;
@@ -422,9 +423,10 @@ template <typename OutT, bool kObserve, int kPipeSIn>
 __global__ void __launch_bounds__(kPipeThreads, 1)
 fe_pipe_kernel(const FeParams p, const FeSeries s, const FeState st, const Consts k, const float *__restrict__ actions,
                OutT *__restrict__ obs, OutT *__restrict__ rewards, int32_t *__restrict__ dones, FeStats *stats,
-               const uint64_t step, const int TE) {
+               const uint64_t step_arg, const uint64_t *__restrict__ step_dev, const int TE) {
     constexpr int RPT = PipeRows<OutT>::value;
     extern __shared__ __align__(128) unsigned char smem[];
+    const uint64_t step = step_dev ? *step_dev : step_arg;
     const int W = p.window;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t ntiles_all = (p.num_envs + TE - 1) / TE;
@@ -578,8 +580,9 @@ template <typename OutT, bool kObserve>
 __global__ void __launch_bounds__(kThreads)
 fe_direct_kernel(const FeParams p, const FeSeries s, const FeState st, const Consts k, const float *__restrict__ actions,
                  OutT *__restrict__ obs, OutT *__restrict__ rewards, int32_t *__restrict__ dones, FeStats *stats,
-                 const uint64_t step) {
+                 const uint64_t step_arg, const uint64_t *__restrict__ step_dev) {
     __shared__ int64_t sh_row0[kThreads];
+    const uint64_t step = step_dev ? *step_dev : step_arg;
     __shared__ OutT sh_pf[kThreads];
     const int W = p.window;
     const int tid = threadIdx.x;
@@ -621,7 +624,8 @@ template <typename OutT, bool kObserve>
 __global__ void __launch_bounds__(kThreads)
 fe_lazy_kernel(const FeParams p, const FeSeries s, const FeState st, const Consts k, const float *__restrict__ actions,
                int64_t *__restrict__ row0_out, OutT *__restrict__ pf_out, OutT *__restrict__ rewards,
-               int32_t *__restrict__ dones, FeStats *stats, const uint64_t step) {
+               int32_t *__restrict__ dones, FeStats *stats, const uint64_t step_arg, const uint64_t *__restrict__ step_dev) {
+    const uint64_t step = step_dev ? *step_dev : step_arg;
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const bool active = i < p.num_envs;
     EnvResult r;
@@ -836,8 +840,10 @@ template <typename OutT, bool kObserve>
 __global__ void __launch_bounds__(kPortThreads)
 fe_portfolio_kernel(const FeParams p, const FeSeries s, const FeState st, const Consts k,
                     const float *__restrict__ actions, OutT *__restrict__ obs, OutT *__restrict__ rewards,
-                    int32_t *__restrict__ dones, FeStats *stats, const uint64_t step, const int CH) {
+                    int32_t *__restrict__ dones, FeStats *stats, const uint64_t step_arg,
+                    const uint64_t *__restrict__ step_dev, const int CH) {
     extern __shared__ __align__(128) unsigned char smem[];
+    const uint64_t step = step_dev ? *step_dev : step_arg;
     const int W = p.window, A = p.num_assets;
     const int tid = threadIdx.x;
     const int64_t i = blockIdx.x;
@@ -1052,7 +1058,7 @@ int env_override(const char *name) {
 
 template <typename OutT, bool kObserve>
 int launch(const FeParams &p, const FeSeries &s, const FeState &st, const float *actions, void *obs, void *rewards,
-           int32_t *dones, FeStats *stats, uint64_t step, cudaStream_t stream) {
+           int32_t *dones, FeStats *stats, uint64_t step, cudaStream_t stream, const uint64_t *step_dev = nullptr) {
     const Consts k = make_consts(p);
     if (p.num_assets > 1 || p.variant == FE_VARIANT_PORTFOLIO) {
         if ((uintptr_t)obs & 15) return FE_EALIGN;
@@ -1071,7 +1077,7 @@ int launch(const FeParams &p, const FeSeries &s, const FeState &st, const float 
             configured[p.device & 15] = true;
         }
         kern<<<(unsigned)p.num_envs, kPortThreads, smem, stream>>>(p, s, st, k, actions, (OutT *)obs, (OutT *)rewards,
-                                                                  dones, stats, step, CH);
+                                                                  dones, stats, step, step_dev, CH);
         return (int)cudaGetLastError();
     }
     static const int no_pipe = env_override("FE_NO_PIPE"); // sweeps: make "auto" fall through to the tile variant
@@ -1099,7 +1105,7 @@ int launch(const FeParams &p, const FeSeries &s, const FeState &st, const float 
             const int64_t ntiles = (p.num_envs + TE - 1) / TE;
             const unsigned blocks = (unsigned)(ntiles < num_sms[dev] ? ntiles : num_sms[dev]);
             kern<<<blocks, kPipeThreads, pipe_smem_bytes<OutT>(TE, p.window, sin), stream>>>(
-                p, s, st, k, actions, (OutT *)obs, (OutT *)rewards, dones, stats, step, TE);
+                p, s, st, k, actions, (OutT *)obs, (OutT *)rewards, dones, stats, step, step_dev, TE);
             return (int)cudaGetLastError();
         }
     }
@@ -1125,14 +1131,17 @@ int launch(const FeParams &p, const FeSeries &s, const FeState &st, const float 
         }
         const int64_t blocks = (p.num_envs + E - 1) / E;
         kern<<<(unsigned)blocks, threads, smem, stream>>>(p, s, st, k, actions, (OutT *)obs, (OutT *)rewards, dones,
-                                                           stats, step, E);
+                                                           stats, step, step_dev, E);
     } else {
         const int64_t blocks = (p.num_envs + kThreads - 1) / kThreads;
         fe_direct_kernel<OutT, kObserve><<<(unsigned)blocks, kThreads, 0, stream>>>(
-            p, s, st, k, actions, (OutT *)obs, (OutT *)rewards, dones, stats, step);
+            p, s, st, k, actions, (OutT *)obs, (OutT *)rewards, dones, stats, step, step_dev);
     }
     return (int)cudaGetLastError();
 }
+
+// step ordinal kept on the device (fe_step_captured): one thread bumps it ahead of the step kernel
+__global__ void fe_bump_kernel(uint64_t *counter) { *counter += 1; }
 
 int set_device(int device) {
     int cur = -1;
@@ -1247,6 +1256,21 @@ int fe_step(const FeParams *p, const FeSeries *s, const FeState *st, const float
                                              step_counter, (cudaStream_t)stream);
 }
 
+int fe_step_captured(const FeParams *p, const FeSeries *s, const FeState *st, const float *actions_dev, void *obs_dev,
+                     void *rewards_dev, int32_t *dones_dev, FeStats *stats_dev, uint64_t *step_counter_dev, void *stream) {
+    int rc = check_common(p, s, st);
+    if (rc) return rc;
+    if (!actions_dev || !obs_dev || !rewards_dev || !dones_dev || !step_counter_dev) return FE_EINVAL;
+    if (stats_dev && !p->evaluate && (!st->ep_return || !st->ep_len)) return FE_EINVAL;
+    if ((rc = set_device(p->device))) return rc;
+    fe_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_counter_dev);
+    if ((rc = (int)cudaGetLastError())) return rc;
+    return p->out_f64 ? launch<double, false>(*p, *s, *st, actions_dev, obs_dev, rewards_dev, dones_dev, stats_dev, 0,
+                                              (cudaStream_t)stream, step_counter_dev)
+                      : launch<float, false>(*p, *s, *st, actions_dev, obs_dev, rewards_dev, dones_dev, stats_dev, 0,
+                                             (cudaStream_t)stream, step_counter_dev);
+}
+
 int fe_observe_lazy(const FeParams *p, const FeSeries *s, const FeState *st, int64_t *obs_row0_dev, void *obs_posfeat_dev,
                     void *stream) {
     int rc = check_common(p, s, st);
@@ -1257,10 +1281,10 @@ int fe_observe_lazy(const FeParams *p, const FeSeries *s, const FeState *st, int
     const unsigned blocks = (unsigned)((p->num_envs + kThreads - 1) / kThreads);
     if (p->out_f64)
         fe_lazy_kernel<double, true><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(
-            *p, *s, *st, k, nullptr, obs_row0_dev, (double *)obs_posfeat_dev, nullptr, nullptr, nullptr, 0);
+            *p, *s, *st, k, nullptr, obs_row0_dev, (double *)obs_posfeat_dev, nullptr, nullptr, nullptr, 0, nullptr);
     else
         fe_lazy_kernel<float, true><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(
-            *p, *s, *st, k, nullptr, obs_row0_dev, (float *)obs_posfeat_dev, nullptr, nullptr, nullptr, 0);
+            *p, *s, *st, k, nullptr, obs_row0_dev, (float *)obs_posfeat_dev, nullptr, nullptr, nullptr, 0, nullptr);
     return (int)cudaGetLastError();
 }
 
@@ -1277,11 +1301,11 @@ int fe_step_lazy(const FeParams *p, const FeSeries *s, const FeState *st, const 
     if (p->out_f64)
         fe_lazy_kernel<double, false><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(
             *p, *s, *st, k, actions_dev, obs_row0_dev, (double *)obs_posfeat_dev, (double *)rewards_dev, dones_dev, stats_dev,
-            step_counter);
+            step_counter, nullptr);
     else
         fe_lazy_kernel<float, false><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(
             *p, *s, *st, k, actions_dev, obs_row0_dev, (float *)obs_posfeat_dev, (float *)rewards_dev, dones_dev, stats_dev,
-            step_counter);
+            step_counter, nullptr);
     return (int)cudaGetLastError();
 }
 

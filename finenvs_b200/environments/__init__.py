@@ -1,1 +1,1 @@
-from .time_series_env import TimeSeriesEnv  # noqa: F401
+from .time_series_env import CapturedRollout, LazyObs, TimeSeriesEnv  # noqa: F401

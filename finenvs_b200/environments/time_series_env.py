@@ -70,6 +70,73 @@ class LazyObs:
         return obs
 
 
+class CapturedRollout:
+    """`num_steps` iterations of `actions = policy(obs); obs, rewards, dones = env.step(actions)` recorded ONCE in a
+    CUDA graph and replayed with a single launch.  The loop it replaces is the reference's evaluation
+    loop (examples/time_series/PPO_LSTM_testing_SPY.py:43-52), whose cost for a few thousand envs is Python and launch
+    overhead, not the step.  The step ordinal lives in device memory (fe_step_captured), so a replay continues the
+    env exactly where eager stepping would be: results are identical to calling env.step() num_steps times.
+
+    Static tensors (overwritten by every replay): `obs` (N, W, 5) current observation, `rewards` (num_steps, N),
+    `dones` (num_steps, N) int32, `actions` (num_steps, N, num_acts)."""
+
+    def __init__(self, env: "TimeSeriesEnv", policy, num_steps: int):
+        if num_steps < 1:
+            raise ValueError("num_steps must be >= 1")
+        self.env, self.policy, self.num_steps = env, policy, int(num_steps)
+        dev, N = env._dev, env.num_envs
+        shape = (N, env.num_intervals * env.num_obs) if env.flat_obs else (N, env.num_intervals, env.num_obs)
+        self.obs = torch.empty(shape, dtype=env.obs_dtype, device=dev)
+        self.rewards = torch.empty((num_steps, N), dtype=env.obs_dtype, device=dev)
+        self.dones = torch.empty((num_steps, N), dtype=torch.int32, device=dev)
+        self.actions = torch.empty((num_steps, N, env.num_acts), dtype=torch.float32, device=dev)
+        self._counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.graph = torch.cuda.CUDAGraph()
+        # warm-up on a side stream (lazy initialisation inside the policy / the library must not be captured), on a
+        # snapshot of the env state that is restored afterwards
+        snap = env.state_snapshot()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            env._observe_into(self.obs)
+            self._counter.fill_(env.step_count)
+            self._record(1)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        env.load_state_snapshot(snap)
+        with torch.cuda.graph(self.graph):
+            self._record(self.num_steps)
+        env.load_state_snapshot(snap)   # capture does not execute, but keep the contract explicit
+
+    def _record(self, steps: int) -> None:
+        env = self.env
+        for t in range(steps):
+            a = self.policy(self.obs)
+            self.actions[t].copy_(a.reshape(env.num_envs, env.num_acts))
+            _lib.check(
+                env._L.fe_step_captured(env._pp, env._ps, env._pst, self.actions[t].data_ptr(), self.obs.data_ptr(),
+                                        self.rewards[t].data_ptr(), self.dones[t].data_ptr(),
+                                        env._stats.data_ptr() if env._stats is not None else None,
+                                        self._counter.data_ptr(), env._stream()),
+                "fe_step_captured",
+            )
+
+    def replay(self, refresh_obs: Optional[bool] = None):
+        """Run the captured num_steps steps.  `refresh_obs=True` first rebuilds `obs` from the env's current state
+        (what env.reset() returns); False continues from the observation the previous replay left (what the eager
+        loop does: the observation returned by a step is built before the auto-reset, :321).  Default: refresh only
+        if this is the first replay or something else stepped / reset the env in between."""
+        env = self.env
+        if refresh_obs is None:
+            refresh_obs = getattr(self, "_resume_at", None) != (env.step_count, env._epoch)
+        if refresh_obs:
+            env._observe_into(self.obs)
+        self._counter.fill_(env.step_count)
+        self.graph.replay()
+        env.step_count += self.num_steps
+        self._resume_at = (env.step_count, env._epoch)
+        return self.obs, self.rewards, self.dones
+
+
 class TimeSeriesEnv(BaseObject):
     def __init__(
         self,
@@ -214,6 +281,7 @@ class TimeSeriesEnv(BaseObject):
         self._ep_len = torch.zeros(N, dtype=torch.int32, device=dev) if self.track_stats else None
         self._stats = torch.zeros(_lib.STATS_BYTES // 8, dtype=torch.int64, device=dev) if need_ep else None
         self.step_count = 0
+        self._epoch = 0   # bumped by everything that changes the state other than a step (reset_all, snapshots)
         self._params = _lib.FeParams(
             N, base, total, self.series.num_rows, self.num_intervals, D, A, int(self.max_shares),
             float(self.starting_balance), float(self.per_share_commission), float(self.initial_margin_requirement),
@@ -392,6 +460,54 @@ class TimeSeriesEnv(BaseObject):
         info_dict = self.record_evaluation_metrics() if self.evaluate else {}
         return (obs, rewards, dones, info_dict)
 
+    # ------------------------------------------------------------------ captured rollouts (8f-4) ----
+    def _observe_into(self, obs: torch.Tensor) -> None:
+        _lib.check(self._L.fe_observe(self._pp, self._ps, self._pst, obs.data_ptr(), self._stream()), "fe_observe")
+
+    _STATE_FIELDS = ("_seg", "_ptr", "_cash", "_long", "_short", "_margin", "_terminated", "_ep_return", "_ep_len", "_stats")
+
+    def state_snapshot(self) -> dict:
+        """Copy of the per-env state (device tensors) + the step ordinal; load_state_snapshot() restores it in place."""
+        snap = {k: getattr(self, k).clone() for k in self._STATE_FIELDS if getattr(self, k, None) is not None}
+        snap["step_count"] = self.step_count
+        return snap
+
+    def load_state_snapshot(self, snap: dict) -> None:
+        for k in self._STATE_FIELDS:
+            if k in snap:
+                getattr(self, k).copy_(snap[k])
+        self.step_count = snap["step_count"]
+        self._epoch += 1
+
+    def capture_rollout(self, policy, num_steps: int) -> CapturedRollout:
+        """Record `num_steps` x (policy -> step) in a CUDA graph; see CapturedRollout."""
+        return CapturedRollout(self, policy, num_steps)
+
+    def evaluate_policy(self, policy, steps_per_replay: int = 32, max_steps: Optional[int] = None,
+                        rollout: Optional[CapturedRollout] = None) -> Dict:
+        """The reference's evaluation loop (PPO_LSTM_testing_SPY.py:43-52: step until info has "returns") with the
+        "all envs terminated" test (:531) read once per `steps_per_replay` graph-replayed steps instead of once per
+        step.  Terminated envs collect zero reward (:527-528), so running past the end changes nothing: the returned
+        {"returns": (N,) f32} equals what the per-step loop returns.  Metrics are reset afterwards (:532-534) — in
+        place, so `rollout` (a CapturedRollout of this env, e.g. the one returned in the result) can be passed back
+        in to evaluate the next checkpoint of the same policy object without capturing again."""
+        if not self.evaluate:
+            raise RuntimeError("evaluate_policy needs an env constructed with evaluate=True")
+        roll = rollout if rollout is not None else self.capture_rollout(policy, steps_per_replay)
+        if roll.env is not self:
+            raise ValueError("rollout was captured on another env")
+        steps = 0
+        while max_steps is None or steps < max_steps:
+            roll.replay(refresh_obs=(steps == 0))
+            steps += roll.num_steps
+            if int(self._stats[1].item()) >= self.num_envs:
+                info = {"returns": self._ep_return.clone(), "steps": steps, "rollout": roll}
+                self._terminated.zero_()
+                self._ep_return.zero_()
+                self._stats.zero_()
+                return info
+        return {"steps": steps, "rollout": roll}
+
     def record_evaluation_metrics(self) -> Dict:
         """:523-536 — the per-env bookkeeping ran inside the kernel; here only the "all terminated"
         test (:531), which like the reference's torch.all() costs one host read per step."""
@@ -411,6 +527,7 @@ class TimeSeriesEnv(BaseObject):
         """Fresh episode for every env (the reset the ES loop expects, cf. isaac_gym_env.py:55-58)."""
         if redraw is None:
             redraw = self.random_reset == "all"
+        self._epoch += 1
         self._launch_reset_all(redraw)
         if self._stats is not None:
             self._stats.zero_()

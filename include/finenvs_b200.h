@@ -130,6 +130,13 @@ int fe_observe(const FeParams *p, const FeSeries *s, const FeState *st, void *ob
 int fe_step(const FeParams *p, const FeSeries *s, const FeState *st, const float *actions_dev, void *obs_dev,
             void *rewards_dev, int32_t *dones_dev, FeStats *stats_dev, uint64_t step_counter, void *stream);
 
+/* fe_step whose step ordinal lives in device memory: the launch first increments *step_counter_dev, then steps
+ * with the new value.  Nothing in the launch depends on a host-side scalar that changes from step to step, so a
+ * policy -> step loop can be captured once in a CUDA graph and replayed (evaluation sweeps, small populations whose
+ * step is launch-bound; replaces the Python loop of examples/time_series/PPO_LSTM_testing_SPY.py:43-52). */
+int fe_step_captured(const FeParams *p, const FeSeries *s, const FeState *st, const float *actions_dev, void *obs_dev,
+                     void *rewards_dev, int32_t *dones_dev, FeStats *stats_dev, uint64_t *step_counter_dev, void *stream);
+
 /* Lazy observations (extension): an observation is fully described by the 12-byte handle (row0, posfeat):
  * obs[i,j,0:4] = logret[row0[i]+j], obs[i,j,4] = posfeat[i] (:428-445).  fe_step_lazy / fe_observe_lazy are fe_step /
  * fe_observe writing the handle instead of the (N,W,5) tensor (single-asset envs); fe_materialize builds the tensor
