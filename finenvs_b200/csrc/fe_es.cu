@@ -236,7 +236,7 @@ fe_es_forward_kernel(const EsLayout lay, const float *__restrict__ theta, const 
 }
 
 // ------------------------------------------------------------------------------------------
-// forward, fast path: first layer 5*R inputs (R <= 64 window rows x 5 features) -> <= 8 outputs — the shape of the ES
+// forward, fast path: first layer 5*R inputs (R <= 63 window rows x 5 features) -> <= 8 outputs — the shape of the ES
 // population rollout on the trading env (BASELINE config 5: 300-8-1).  ncu on the generic kernel above
 // (profiles/r01_es_forward_generic_ncu.txt): 1.08 ms per 512 Ki envs, 1.65 TB/s, stalled on its own eps loads
 // (long scoreboard 10.6 of 12.7 stall cycles per issue, <= 1 KB in flight per warp).  Here
@@ -266,6 +266,7 @@ struct FastShape {
     int eps_bytes;   // P_pad * 2
     int stage_bytes; // eps + 2 x + pf pair, rounded to 128
     int act_stride;  // floats per sign in the activation buffers of layers >= 1
+    int tail_in_regs; // exactly two layers and <= 8 actions: the second layer runs out of the butterfly's registers
     int theta_bytes; // P_pad * 4 rounded to 128
 };
 __host__ __device__ inline size_t fast_smem_bytes(const FastShape &f) {
@@ -296,7 +297,8 @@ fe_es_forward_fast_kernel(const EsLayout lay, const FastShape fs, const float *_
     mbar_fence_init();
     __syncthreads();
 
-    // lane-stationary first-layer theta: rows lane and lane + 32, five inputs each, eight outputs (packed index j*8 + o)
+    // lane-stationary first-layer theta: window rows lane and lane + 32 (inputs 5r .. 5r+4, packed index j*8 + o).
+    // "Row" R is the bias: its first input is the constant 1 (packed row j = I), the other four do not exist.
     float t0[2][5][8];
 #pragma unroll
     for (int sl = 0; sl < 2; ++sl) {
@@ -304,12 +306,12 @@ fe_es_forward_fast_kernel(const EsLayout lay, const FastShape fs, const float *_
 #pragma unroll
         for (int i = 0; i < 5; ++i)
 #pragma unroll
-            for (int o = 0; o < 8; ++o) t0[sl][i][o] = r < R ? th[(size_t)(5 * r + i) * 8 + o] : 0.0f;
+            for (int o = 0; o < 8; ++o) t0[sl][i][o] = (r < R || (r == R && i == 0)) ? th[(size_t)(5 * r + i) * 8 + o] : 0.0f;
     }
 
     const int64_t units = num_pairs + num_eval;
     const int64_t gw = (int64_t)blockIdx.x * kFastWarps + warp, nw = (int64_t)gridDim.x * kFastWarps;
-    const int64_t nloc = gw < units ? (units - gw + nw - 1) / nw : 0;
+    const int nloc = gw < units ? (int)((units - gw + nw - 1) / nw) : 0;
     auto env_of = [&](int64_t u, int sgn) -> int64_t { // :121-136 positives first, negatives second, eval envs last
         if (u >= num_pairs) return 2 * num_pairs + (u - num_pairs);
         return sgn ? u + num_pairs : u;
@@ -317,19 +319,21 @@ fe_es_forward_fast_kernel(const EsLayout lay, const FastShape fs, const float *_
     // registers of lanes 0/1 describing the NEXT unit to issue (loaded one iteration early: no stall on row0)
     int64_t n_src = 0;
     float n_pf = 0.0f;
-    auto preload = [&](int64_t k) {
+    auto preload = [&](int k) {
         if (k < nloc && lane < 2) {
-            const int64_t e = env_of(gw + k * nw, lane);
+            const int64_t e = env_of(gw + (int64_t)k * nw, lane);
             if (kLazy) { n_src = __ldg(row0 + e); n_pf = __ldg(posfeat + e); }
             else n_src = e;
         }
     };
-    auto issue = [&](int64_t k) {
+    int st_i = 0; // stage the next issue goes to
+    auto issue = [&](int k) {
         if (k >= nloc) return;
-        const int64_t u = gw + k * nw;
+        const int64_t u = gw + (int64_t)k * nw;
         const bool is_eval = u >= num_pairs;
-        unsigned char *stage = ring + (size_t)(k % kFastStages) * fs.stage_bytes;
-        const uint32_t bar = bar0 + 8u * (uint32_t)(k % kFastStages);
+        unsigned char *stage = ring + (size_t)st_i * fs.stage_bytes;
+        const uint32_t bar = bar0 + 8u * (uint32_t)st_i;
+        st_i = st_i + 1 == kFastStages ? 0 : st_i + 1;
         if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)((is_eval ? 0 : fs.eps_bytes) + 2 * fs.x_bytes));
         __syncwarp();
         if (lane == 0 && !is_eval) bulk_load(smem_u32(stage), eps + u * P, (uint32_t)fs.eps_bytes, bar);
@@ -340,18 +344,22 @@ fe_es_forward_fast_kernel(const EsLayout lay, const FastShape fs, const float *_
             if (kLazy) reinterpret_cast<float *>(stage + fs.eps_bytes + 2 * fs.x_bytes)[lane] = n_pf;
         }
     };
-    for (int64_t k = 0; k < kFastStages - 1; ++k) { preload(k); issue(k); }
+    for (int k = 0; k < kFastStages - 1; ++k) { preload(k); issue(k); }
     preload(kFastStages - 1);
 
-    for (int64_t k = 0; k < nloc; ++k) {
+    const int m = lane >> 1, om = m & 7;                 // after the butterfly: lanes 2m, 2m+1 hold value m = sign*8 + output
+    const int off1 = (int)lay.off[1];
+    int st_c = 0;
+    uint32_t ph_c = 0;
+    for (int k = 0; k < nloc; ++k) {
         issue(k + kFastStages - 1); // into the stage consumed in iteration k - 1
         preload(k + kFastStages);
-        const int64_t unit = gw + k * nw;
+        const int64_t unit = gw + (int64_t)k * nw;
         const bool is_eval = unit >= num_pairs;
-        const int64_t e0 = env_of(unit, 0), e1 = env_of(unit, 1);
         const float sg = is_eval ? 0.0f : sigma;
-        const unsigned char *stage = ring + (size_t)(k % kFastStages) * fs.stage_bytes;
-        mbar_wait(bar0 + 8u * (uint32_t)(k % kFastStages), (uint32_t)((k / kFastStages) & 1));
+        const unsigned char *stage = ring + (size_t)st_c * fs.stage_bytes;
+        mbar_wait(bar0 + 8u * (uint32_t)st_c, ph_c);
+        if (++st_c == kFastStages) { st_c = 0; ph_c ^= 1u; }
         __syncwarp();
         const unsigned char *xs = stage + fs.eps_bytes;
         // ---- layer 0
@@ -361,7 +369,8 @@ fe_es_forward_fast_kernel(const EsLayout lay, const FastShape fs, const float *_
 #pragma unroll
         for (int sl = 0; sl < 2; ++sl) {
             const int r = lane + 32 * sl;
-            if (r < R) {
+            if (r <= R) {
+                const bool row = r < R;
                 float xp[5], xm[5];
                 if (kLazy) {
                     const float4 p4 = *reinterpret_cast<const float4 *>(xs + (size_t)r * 16);
@@ -376,10 +385,15 @@ fe_es_forward_fast_kernel(const EsLayout lay, const FastShape fs, const float *_
                     for (int i = 0; i < 5; ++i) { xp[i] = pp[i]; xm[i] = pm[i]; }
                 }
 #pragma unroll
+                for (int i = 0; i < 5; ++i) { // the bias "row": (1, 0, 0, 0, 0) whatever lies behind the window
+                    xp[i] = row ? xp[i] : (i == 0 ? 1.0f : 0.0f);
+                    xm[i] = row ? xm[i] : (i == 0 ? 1.0f : 0.0f);
+                }
+#pragma unroll
                 for (int i = 0; i < 5; ++i) {
                     float e[8];
                     uint4 ev = make_uint4(0u, 0u, 0u, 0u);
-                    if (!is_eval) ev = *reinterpret_cast<const uint4 *>(stage + (size_t)(5 * r + i) * 16);
+                    if (!is_eval && (row || i == 0)) ev = *reinterpret_cast<const uint4 *>(stage + (size_t)(5 * r + i) * 16);
                     halves8_to_floats(ev, e);
 #pragma unroll
                     for (int o = 0; o < 8; ++o) {
@@ -389,17 +403,6 @@ fe_es_forward_fast_kernel(const EsLayout lay, const FastShape fs, const float *_
                         b1[o] = fmaf(e[o], xm[i], b1[o]);
                     }
                 }
-            }
-        }
-        if (lane == 0) { // bias row (input == 1)
-            float e[8];
-            uint4 ev = make_uint4(0u, 0u, 0u, 0u);
-            if (!is_eval) ev = *reinterpret_cast<const uint4 *>(stage + (size_t)I * 16);
-            halves8_to_floats(ev, e);
-#pragma unroll
-            for (int o = 0; o < 8; ++o) {
-                const float t = th[(size_t)I * 8 + o];
-                a0[o] += t; a1[o] += t; b0[o] += e[o]; b1[o] += e[o];
             }
         }
         float v[16];
@@ -413,13 +416,63 @@ fe_es_forward_fast_kernel(const EsLayout lay, const FastShape fs, const float *_
         butterfly_step<2>(v, lane);
         butterfly_step<1>(v, lane);
         v[0] += __shfl_xor_sync(kAll, v[0], 1);
+        const int64_t e0 = env_of(unit, 0), e1 = env_of(unit, 1);
+        if (fs.tail_in_regs) {
+            // ---- second (= last) layer with <= 8 outputs, straight from the butterfly's registers: lane pair m holds
+            // hidden unit om of sign m>>3 (hidden "unit" out0 is the constant 1 feeding the bias row); the dot product
+            // over the 8 lane pairs of one sign is three xor-shuffles per output
+            const float h = om < out0 ? tanhf(v[0]) : (om == out0 ? 1.0f : 0.0f);
+            const float sgs = (m >> 3) ? -sg : sg;
+            float t[8], e[8];
+            {
+                float4 t03 = make_float4(0.f, 0.f, 0.f, 0.f), t47 = t03;
+                uint4 ev = make_uint4(0u, 0u, 0u, 0u);
+                if (om <= out0) {
+                    t03 = *reinterpret_cast<const float4 *>(th + off1 + om * 8);
+                    t47 = *reinterpret_cast<const float4 *>(th + off1 + om * 8 + 4);
+                    if (!is_eval) ev = *reinterpret_cast<const uint4 *>(stage + (size_t)(off1 + om * 8) * 2);
+                }
+                t[0] = t03.x; t[1] = t03.y; t[2] = t03.z; t[3] = t03.w; t[4] = t47.x; t[5] = t47.y; t[6] = t47.z; t[7] = t47.w;
+                halves8_to_floats(ev, e);
+            }
+            float bias_t = 0.0f, bias_e = 0.0f; // out0 == 8: the bias row has no lane pair of its own
+#pragma unroll
+            for (int o2 = 0; o2 < 8; ++o2) {
+                if (o2 < OL) {
+                    float pacc = fmaf(sgs, e[o2], t[o2]) * h;
+                    pacc += __shfl_xor_sync(kAll, pacc, 2);
+                    pacc += __shfl_xor_sync(kAll, pacc, 4);
+                    pacc += __shfl_xor_sync(kAll, pacc, 8);
+                    if (out0 == 8) {
+                        bias_t = th[off1 + 64 + o2];
+                        bias_e = is_eval ? 0.0f : __half2float(*reinterpret_cast<const __half *>(stage + (size_t)(off1 + 64 + o2) * 2));
+                        pacc += fmaf(sgs, bias_e, bias_t);
+                    }
+                    float a = tanhf(pacc);
+                    const bool writer = (lane & 15) == 0 && !(lane == 16 && is_eval);
+                    if (writer) {
+                        const int64_t e = lane ? e1 : e0;
+                        if (noise_std > 0.0f && !is_eval && num_eval > 0) {
+                            uint32_t rr[4];
+                            philox4x32_10(seed ^ kEsKey, (uint64_t)(env_id_base + e), step | ((uint64_t)(o2 >> 2) << 48), 0u, rr);
+                            float z[4];
+                            box_muller(rr[0], rr[1], z[0], z[1]);
+                            box_muller(rr[2], rr[3], z[2], z[3]);
+                            a = fmaf(noise_std, (o2 & 2) ? ((o2 & 1) ? z[3] : z[2]) : ((o2 & 1) ? z[1] : z[0]), a);
+                        }
+                        actions[e * OL + o2] = a;
+                    }
+                }
+            }
+            __syncwarp(); // every lane is done with this stage
+            continue;
+        }
         {
-            const int m = lane >> 1, o = m & 7;
-            if ((lane & 1) == 0 && o < out0) bufA[(m >> 3) * stride + o] = tanhf(v[0]);
+            if ((lane & 1) == 0 && om < out0) bufA[(m >> 3) * stride + om] = tanhf(v[0]);
             if (lane == 0) { bufA[out0] = 1.0f; bufA[stride + out0] = 1.0f; }
         }
         __syncwarp();
-        // ---- layers 1 .. L-1: theta from shared memory, eps from the stage
+        // ---- layers 1 .. L-1 (general shapes): theta from shared memory, eps from the stage
         float *xin = bufA, *xout = bufB;
         for (int l = 1; l < lay.L; ++l) {
             const int in1 = lay.in[l] + 1, out = lay.out[l];
@@ -458,7 +511,7 @@ fe_es_forward_fast_kernel(const EsLayout lay, const FastShape fs, const float *_
                 butterfly_step<2>(w, lane);
                 butterfly_step<1>(w, lane);
                 w[0] += __shfl_xor_sync(kAll, w[0], 1);
-                const int m = lane >> 1, o = c * 8 + (m & 7);
+                const int o = c * 8 + om;
                 if ((lane & 1) == 0 && o < out) xout[(m >> 3) * stride + o] = tanhf(w[0]);
             }
             if (lane == 0) { xout[out] = 1.0f; xout[stride + out] = 1.0f; }
@@ -623,7 +676,7 @@ int fe_es_forward(const FeEsNet *net, const float *theta_packed_dev, const void 
     const int64_t P = lay.off[lay.L];
     // ---- fast path: 5R -> <= 8 first layer (R <= 64), inputs 16-byte granular, ring fits in shared memory
     static const bool no_fast = getenv("FE_ES_NO_FAST") != nullptr; // A/B runs and the generic kernel's tests
-    if (!no_fast && lay.out[0] <= 8 && lay.in[0] % 5 == 0 && lay.in[0] / 5 <= 64 &&
+    if (!no_fast && lay.out[0] <= 8 && lay.in[0] % 5 == 0 && lay.in[0] / 5 <= 63 &&
         (lazy || (lay.in[0] % 4 == 0 && ((uintptr_t)obs_dev & 15) == 0))) {
         FastShape f;
         f.rows = lay.in[0] / 5;
@@ -633,6 +686,7 @@ int fe_es_forward(const FeEsNet *net, const float *theta_packed_dev, const void 
         int md = 1;
         for (int l = 1; l <= lay.L; ++l) md = lay.out[l - 1] > md ? lay.out[l - 1] : md;
         f.act_stride = (md + 1 + 3) & ~3;
+        f.tail_in_regs = lay.L == 2 && lay.out[1] <= 8;
         f.theta_bytes = (int)((P * 4 + 127) & ~(int64_t)127);
         const size_t smem = fast_smem_bytes(f);
         if (smem <= 226 * 1024) {
