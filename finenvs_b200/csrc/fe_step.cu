@@ -48,6 +48,9 @@ __device__ __forceinline__ double relu64(double x) { return x < 0.0 ? 0.0 : x; }
 struct Consts {
     float ms, scale, cf, imrf, SBf;
     double c, imr, mmr1, SB;
+    // optional second destination of rewards / dones (fe_step_host's zero-copy mode: mapped pinned host memory)
+    void *rewards_mirror;
+    int32_t *dones_mirror;
 };
 
 Consts make_consts(const FeParams &p) {
@@ -61,6 +64,8 @@ Consts make_consts(const FeParams &p) {
     k.imr = p.imr;
     k.mmr1 = 1.0 + p.mmr;                          // :462
     k.SB = p.starting_balance;
+    k.rewards_mirror = nullptr;
+    k.dones_mirror = nullptr;
     return k;
 }
 
@@ -223,6 +228,7 @@ __device__ __forceinline__ EnvResult env_step(const FeParams &p, const FeSeries 
     st.ptr[i] = ptr; st.cash[i] = cash; st.long_sh[i] = lng; st.short_sh[i] = sht; st.margin[i] = margin;
     rewards[i] = (OutT)rew;
     dones[i] = done; // :296 dones.int()
+    if (k.dones_mirror) { reinterpret_cast<OutT *>(k.rewards_mirror)[i] = (OutT)rew; k.dones_mirror[i] = done; }
     return res;
 }
 
@@ -827,6 +833,7 @@ __device__ __forceinline__ void portfolio_step(const FeParams &p, const FeSeries
         st.seg[i] = seg; st.ptr[i] = ptr; st.cash[i] = cash;
         rewards[i] = (OutT)rew;
         dones[i] = done;
+        if (k.dones_mirror) { reinterpret_cast<OutT *>(k.rewards_mirror)[i] = (OutT)rew; k.dones_mirror[i] = done; }
     }
 }
 
@@ -1058,8 +1065,11 @@ int env_override(const char *name) {
 
 template <typename OutT, bool kObserve>
 int launch(const FeParams &p, const FeSeries &s, const FeState &st, const float *actions, void *obs, void *rewards,
-           int32_t *dones, FeStats *stats, uint64_t step, cudaStream_t stream, const uint64_t *step_dev = nullptr) {
-    const Consts k = make_consts(p);
+           int32_t *dones, FeStats *stats, uint64_t step, cudaStream_t stream, const uint64_t *step_dev = nullptr,
+           void *rewards_mirror = nullptr, int32_t *dones_mirror = nullptr) {
+    Consts k = make_consts(p);
+    k.rewards_mirror = rewards_mirror;
+    k.dones_mirror = dones_mirror;
     if (p.num_assets > 1 || p.variant == FE_VARIANT_PORTFOLIO) {
         if ((uintptr_t)obs & 15) return FE_EALIGN;
         const int P = p.window * p.num_assets;
@@ -1336,11 +1346,35 @@ int fe_step_host(const FeParams *p, const FeSeries *s, const FeState *st, const 
     int rc = check_common(p, s, st);
     if (rc) return rc;
     if (!obs_dev || !rewards_dev || !dones_dev) return FE_EINVAL;
+    if (stats_dev && !p->evaluate && (!st->ep_return || !st->ep_len)) return FE_EINVAL;
     if ((rc = set_device(p->device))) return rc;
     cudaStream_t q = (cudaStream_t)stream;
     const int64_t n = p->num_envs;
     const int A = p->num_assets;
     const size_t osz = p->out_f64 ? 8 : 4;
+    // Zero-copy mode: when all three host buffers are pinned (mapped into the device's address space), the step
+    // kernel reads the actions from them and writes rewards / dones to them directly over PCIe — 12 bytes per env
+    // spread over the whole kernel, no copy-engine hop, no head (upload) or tail (download) outside the kernel.
+    // rewards_dev / dones_dev are written as well (device-side consumers); actions_dev is left untouched.
+    static const int no_zc = env_override("FE_HOST_NO_ZEROCOPY");
+    if (!no_zc) {
+        cudaPointerAttributes aa, ar, ad;
+        const bool ok = cudaPointerGetAttributes(&aa, actions_host) == cudaSuccess && aa.type == cudaMemoryTypeHost &&
+                        aa.devicePointer && cudaPointerGetAttributes(&ar, rewards_host) == cudaSuccess &&
+                        ar.type == cudaMemoryTypeHost && ar.devicePointer &&
+                        cudaPointerGetAttributes(&ad, dones_host) == cudaSuccess && ad.type == cudaMemoryTypeHost &&
+                        ad.devicePointer;
+        (void)cudaGetLastError(); // an unregistered pointer leaves a sticky-free error on old drivers
+        if (ok) {
+            const float *a = (const float *)aa.devicePointer;
+            rc = p->out_f64 ? launch<double, false>(*p, *s, *st, a, obs_dev, rewards_dev, dones_dev, stats_dev, step_counter, q,
+                                                    nullptr, ar.devicePointer, (int32_t *)ad.devicePointer)
+                            : launch<float, false>(*p, *s, *st, a, obs_dev, rewards_dev, dones_dev, stats_dev, step_counter, q,
+                                                   nullptr, ar.devicePointer, (int32_t *)ad.devicePointer);
+            if (rc) return rc;
+            return (int)cudaStreamSynchronize(q);
+        }
+    }
     static const int ov_chunks = env_override("FE_HOST_CHUNKS");
     int chunks = ov_chunks > 0 ? ov_chunks : 4;
     int64_t per = ((n + chunks - 1) / chunks + 1023) & ~(int64_t)1023;

@@ -149,9 +149,12 @@ int fe_step_lazy(const FeParams *p, const FeSeries *s, const FeState *st, const 
 int fe_materialize(const FeParams *p, const FeSeries *s, const int64_t *obs_row0_dev, const void *obs_posfeat_dev,
                    void *obs_dev, void *stream);
 
-/* Same step driven from HOST buffers (the call a non-torch embedder makes): copies actions host->device,
- * runs fe_step, copies rewards and dones device->host and waits for them.  The observation stays in HBM
- * (obs_dev) for the policy.  actions_host/rewards_host/dones_host should be pinned for full speed. */
+/* Same step driven from HOST buffers (the call a non-torch embedder makes).  When actions_host, rewards_host and
+ * dones_host are all pinned (cudaHostAlloc / cudaHostRegister), the step kernel itself reads the actions from and
+ * writes rewards / dones to host memory over PCIe (zero-copy: no separate upload or download); otherwise the envs
+ * are cut into chunks whose upload, kernel and download are pipelined over three streams.  Either way the call
+ * returns after the results are in rewards_host / dones_host; rewards_dev / dones_dev hold the same values; the
+ * observation stays in HBM (obs_dev) for the policy.  actions_dev is scratch (N*A floats). */
 int fe_step_host(const FeParams *p, const FeSeries *s, const FeState *st, const float *actions_host,
                  float *actions_dev, void *obs_dev, void *rewards_dev, int32_t *dones_dev, void *rewards_host,
                  int32_t *dones_host, FeStats *stats_dev, uint64_t step_counter, void *stream);

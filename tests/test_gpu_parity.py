@@ -496,6 +496,7 @@ def test_step_host_pipeline_equals_device_step(N, A, dtype):
         o2, r2, d2, _ = b_env.step_host(a.pin_memory() if t % 2 else a)
         assert r2.device.type == "cpu" and d2.device.type == "cpu"
         assert torch.equal(o1, o2) and torch.equal(r1.cpu(), r2) and torch.equal(d1.cpu(), d2)
+        assert torch.equal(b_env._host_bufs[1], r1) and torch.equal(b_env._host_bufs[2], d1)   # device copies too
         for k in ("_seg", "_ptr", "_cash", "_long", "_short", "_margin"):
             assert torch.equal(getattr(a_env, k), getattr(b_env, k)), k
     sa, sb = a_env.stats(), b_env.stats()
