@@ -478,7 +478,12 @@ fe_pipe_kernel(const FeParams p, const FeSeries s, const FeState st, const Const
     } else {
         // ------------------------------------------------------------------ movers
         const int mtid = tid - kPipeBook * 32;
-        const float invW = 1.0f / (float)W;
+        int e_u[RPT], j_u[RPT]; // tile row mtid + u*kMovers = window row j_u of env e_u: the same in every tile
+#pragma unroll
+        for (int u = 0; u < RPT; ++u) {
+            e_u[u] = (mtid + u * kMovers) / W;
+            j_u[u] = (mtid + u * kMovers) - e_u[u] * W;
+        }
         const Row4<OutT> *series_rows = reinterpret_cast<const Row4<OutT> *>(s.logret);
         auto tile_rows = [&](int t) {
             const int64_t env0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TE;
@@ -495,8 +500,7 @@ fe_pipe_kernel(const FeParams p, const FeSeries s, const FeState st, const Const
             for (int u = 0; u < RPT; ++u) {
                 const int r = mtid + u * kMovers;
                 if (r < nrows) {
-                    const int e = __float2int_rz(((float)r + 0.5f) * invW);
-                    const Row4<OutT> *src = series_rows + d_row0[q * TE + e] + (r - e * W);
+                    const Row4<OutT> *src = series_rows + d_row0[q * TE + e_u[u]] + j_u[u];
                     if constexpr (kPipeSIn == 0) {
                         buf[u] = ldg_row(src);
                     } else {
@@ -540,14 +544,13 @@ fe_pipe_kernel(const FeParams p, const FeSeries s, const FeState st, const Const
             for (int u = 0; u < RPT; ++u) {
                 const int r = mtid + u * kMovers;
                 if (r < nrows) {
-                    const int e = __float2int_rz(((float)r + 0.5f) * invW);
                     OutT *o = out_tile + (size_t)r * 5;
                     if constexpr (sizeof(OutT) == 4) {
                         o[0] = cur[u].v.x; o[1] = cur[u].v.y; o[2] = cur[u].v.z; o[3] = cur[u].v.w;
                     } else {
                         o[0] = cur[u].a.x; o[1] = cur[u].a.y; o[2] = cur[u].b.x; o[3] = cur[u].b.y;
                     }
-                    o[4] = pf[e];
+                    o[4] = pf[e_u[u]];
                 }
             }
             const size_t out_bytes = (size_t)nrows * 5 * sizeof(OutT);
@@ -576,6 +579,184 @@ fe_pipe_kernel(const FeParams p, const FeSeries s, const FeState st, const Const
             }
         }
         if (mtid == 0) bulk_wait_read_all();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// scatter variant: the pipe variant without register staging.  ncu on the pipe kernel's "cached" flavour
+// (profiles/r01_v3_pipe_ncu_full_c2.txt) shows nothing saturated — DRAM 58 %, L1->XBAR 63 %, LSU 40 % — while a plain
+// fill of the same 1.26 GB runs at 7.4 TB/s: the movers' read side is bounded by what their registers can keep in
+// flight (one tile, ~30 KB per SM).  Here the window elements travel global -> shared memory with element-sized
+// asynchronous copies (cp.async, SASS LDGSTS) that land DIRECTLY at their interleaved position in the output tile
+// (element i of an env's window goes to i + i/4: the 4 -> 5 interleave is the scatter's address pattern); the movers
+// only add the position feature column.  Nothing passes through registers, so the bytes in flight are bounded by the
+// shared-memory ring (kScDepth tiles ahead), not by the register file.  Roles per block (one block per SM):
+//   bookkeeper warps: as in the pipe variant (descriptor ring of {row0, position feature});
+//   mover warps: issue the copies of tile t, then retire tile t - depth (cp.async.wait_group, proxy fence, arrive);
+//   one store warp: waits for a tile to be complete, issues its bulk async store (UBLKCP.G.S), frees the stage of the
+//                   store before it once that one has been read out.
+// ------------------------------------------------------------------------------------------
+#ifndef FE_SC_BOOK
+#define FE_SC_BOOK 6
+#endif
+#ifndef FE_SC_MOVE
+#define FE_SC_MOVE 8
+#endif
+constexpr int kScBook = FE_SC_BOOK;
+constexpr int kScMove = FE_SC_MOVE;
+constexpr int kScThreads = (kScBook + kScMove + 1) * 32;
+constexpr int kScMovers = kScMove * 32;
+constexpr int kScQ = 8;        // descriptor ring depth
+constexpr int kScMaxStages = 8;
+
+template <typename OutT> __host__ __device__ inline size_t scatter_smem_bytes(int TE, int W, int stages) {
+    return 256 + (size_t)kScQ * TE * 16 + (size_t)stages * (((size_t)TE * W * 5 * sizeof(OutT) + 127) & ~(size_t)127);
+}
+template <int kBytes> __device__ __forceinline__ void cp_async_elem(uint32_t dst_smem, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst_smem), "l"(src), "n"(kBytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_dyn(int n) { // wait until at most n of this thread's groups are pending
+    switch (n) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+    case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+    }
+}
+
+template <typename OutT, bool kObserve>
+__global__ void __launch_bounds__(kScThreads, 1)
+fe_scatter_kernel(const FeParams p, const FeSeries s, const FeState st, const Consts k, const float *__restrict__ actions,
+                  OutT *__restrict__ obs, OutT *__restrict__ rewards, int32_t *__restrict__ dones, FeStats *stats,
+                  const uint64_t step_arg, const uint64_t *__restrict__ step_dev, const int TE, const int S, const int D) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint64_t step = step_dev ? *step_dev : step_arg;
+    const int W = p.window;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t ntiles_all = (p.num_envs + TE - 1) / TE;
+    const int ntiles = (int)((ntiles_all - blockIdx.x + gridDim.x - 1) / gridDim.x);
+    const uint32_t bars = smem_u32(smem);
+    auto desc_full = [&](int q) { return bars + 8u * q; };
+    auto desc_free = [&](int q) { return bars + 8u * (kScQ + q); };
+    auto tile_ready = [&](int si) { return bars + 8u * (2 * kScQ + si); };
+    auto stage_free = [&](int si) { return bars + 8u * (2 * kScQ + kScMaxStages + si); };
+    int64_t *d_row0 = reinterpret_cast<int64_t *>(smem + 256);                      // [Q][TE]
+    double *d_pf = reinterpret_cast<double *>(smem + 256 + (size_t)kScQ * TE * 8);  // [Q][TE], OutT in the low bytes
+    const size_t stage_bytes = ((size_t)TE * W * 5 * sizeof(OutT) + 127) & ~(size_t)127;
+    unsigned char *ring = smem + 256 + (size_t)kScQ * TE * 16;
+    auto tile_env0 = [&](int t) { return ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TE; };
+
+    if (tid == 0) {
+        for (int q = 0; q < kScQ; ++q) { mbar_init(desc_full(q), 1); mbar_init(desc_free(q), kScMove); }
+        for (int si = 0; si < kScMaxStages; ++si) { mbar_init(tile_ready(si), kScMove); mbar_init(stage_free(si), 1); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp < kScBook) {
+        // ------------------------------------------------------------------ bookkeepers
+        for (int t = warp; t < ntiles; t += kScBook) {
+            const int q = t % kScQ;
+            mbar_wait(desc_free(q), ((t / kScQ) & 1) ^ 1); // first lap passes immediately
+            const int64_t env0 = tile_env0(t);
+            const int nvalid = (int)min((int64_t)TE, p.num_envs - env0);
+            EnvResult r;
+            r.done = 0; r.newly_terminated = 0; r.fin_return = 0.0; r.fin_len = 0; r.row0 = 0; r.posfeat = 0.0;
+            const bool active = lane < nvalid;
+            if (active) {
+                const int64_t i = env0 + lane;
+                if (kObserve) r = env_observe(p, s, st, k, i);
+                else r = env_step<OutT>(p, s, st, k, i, actions, rewards, dones, stats != nullptr, step);
+                d_row0[q * TE + lane] = r.row0;
+                reinterpret_cast<OutT *>(d_pf + q * TE)[lane] = (OutT)r.posfeat;
+            }
+            if (!kObserve) accumulate_stats(stats, r, active);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(desc_full(q));
+        }
+    } else if (warp < kScBook + kScMove) {
+        // ------------------------------------------------------------------ movers
+        const int mt = tid - kScBook * 32;
+        const int W4 = W * 4, W5 = W * 5;
+        const int step_e4 = kScMovers / W4, step_i4 = kScMovers % W4; // element walk: idx += kScMovers
+        const int step_eW = kScMovers / W, step_jW = kScMovers % W;   // row walk
+        const OutT *lr = reinterpret_cast<const OutT *>(s.logret);
+        auto retire = [&](int tt, int pending) { // tile tt's copies of this thread have landed -> visible to the bulk store
+            cp_async_wait_dyn(pending);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tile_ready(tt % S));
+        };
+        for (int t = 0; t < ntiles; ++t) {
+            const int q = t % kScQ, si = t % S;
+            mbar_wait(desc_full(q), (t / kScQ) & 1);
+            if (t >= S) mbar_wait(stage_free(si), ((t / S) - 1) & 1);
+            const int nvalid = (int)min((int64_t)TE, p.num_envs - tile_env0(t));
+            unsigned char *stage = ring + (size_t)si * stage_bytes;
+            const uint32_t stage_u32 = smem_u32(stage);
+            const int64_t *row0s = d_row0 + q * TE;
+            { // window elements: element i of env e -> out element e*W5 + i + i/4
+                int e = mt / W4, i = mt - e * W4;
+                while (e < nvalid) {
+                    const OutT *src = lr + row0s[e] * 4 + i;
+                    cp_async_elem<sizeof(OutT)>(stage_u32 + (uint32_t)(e * W5 + i + (i >> 2)) * (uint32_t)sizeof(OutT), src);
+                    e += step_e4; i += step_i4;
+                    if (i >= W4) { i -= W4; ++e; }
+                }
+            }
+            { // position feature column
+                const OutT *pf = reinterpret_cast<const OutT *>(d_pf + q * TE);
+                OutT *out = reinterpret_cast<OutT *>(stage);
+                int e = mt / W, j = mt - e * W;
+                while (e < nvalid) {
+                    out[(e * W + j) * 5 + 4] = pf[e];
+                    e += step_eW; j += step_jW;
+                    if (j >= W) { j -= W; ++e; }
+                }
+            }
+            cp_async_commit();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(desc_free(q)); // this warp has consumed the descriptor
+            if (t >= D) retire(t - D, D);
+        }
+        for (int tt = ntiles > D ? ntiles - D : 0; tt < ntiles; ++tt) retire(tt, ntiles - 1 - tt);
+    } else {
+        // ------------------------------------------------------------------ store warp
+        for (int t = 0; t < ntiles; ++t) {
+            const int si = t % S;
+            mbar_wait(tile_ready(si), (t / S) & 1);
+            const int64_t env0 = tile_env0(t);
+            const int nvalid = (int)min((int64_t)TE, p.num_envs - env0);
+            const size_t out_bytes = (size_t)nvalid * W * 5 * sizeof(OutT);
+            OutT *dst = obs + (size_t)env0 * W * 5;
+            const unsigned char *stage = ring + (size_t)si * stage_bytes;
+            if ((out_bytes & 15) == 0) {
+                if (lane == 0) {
+                    bulk_store(dst, smem_u32(stage), (uint32_t)out_bytes);
+                    bulk_commit();
+                    if (t >= 1) { // at most this store still reading: the one before it has left shared memory
+                        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        mbar_arrive(stage_free((t - 1) % S));
+                    }
+                }
+            } else { // ragged last tile: plain stores, synchronous
+                const OutT *src = reinterpret_cast<const OutT *>(stage);
+                for (int f = lane; f < nvalid * W * 5; f += 32) dst[f] = src[f];
+                __syncwarp();
+                if (lane == 0) {
+                    if (t >= 1) {
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        mbar_arrive(stage_free((t - 1) % S));
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (lane == 0) bulk_wait_read_all();
     }
 }
 
@@ -1041,6 +1222,32 @@ int pick_tile_envs(int W, bool f64, int *threads_out = nullptr) {
     return (int)e;
 }
 
+// tuning overrides (sweeps only)
+int env_override(const char *name) {
+    const char *v = getenv(name);
+    return v ? atoi(v) : 0;
+}
+
+// scatter variant: envs per tile (<= 32, multiple of 4), ring stages S (4..8) and fill depth D = S - 3
+// (D + 1 tiles being filled / landing, up to 2 being stored); false = window too large
+bool pick_scatter(int W, bool f64, int *TE, int *S, int *D) {
+    static const int ov_te = env_override("FE_SC_TE"), ov_s = env_override("FE_SC_STAGES"), ov_d = env_override("FE_SC_DEPTH");
+    int te = 32;
+    if (ov_te >= 4) te = ov_te & ~3;
+    if (te > 32) te = 32;
+    auto bytes = [&](int t, int st) { return f64 ? scatter_smem_bytes<double>(t, W, st) : scatter_smem_bytes<float>(t, W, st); };
+    while (te >= 4 && bytes(te, 4) > (size_t)kSmemMax) te -= 4;
+    if (te < 4) return false;
+    int st = kScMaxStages;
+    while (st > 4 && bytes(te, st) > (size_t)kSmemMax) --st;
+    if (ov_s >= 4 && ov_s <= st) st = ov_s;
+    int d = st - 3;
+    if (ov_d >= 1 && ov_d <= st - 2) d = ov_d;
+    if (d > 6) d = 6;
+    *TE = te; *S = st; *D = d;
+    return true;
+}
+
 // envs per tile of the pipe variant: up to 32 (one bookkeeper lane each), a multiple of 4 (16-byte store
 // granularity), with TE*W rows fitting the movers' register staging; 0 = window too large, use the tile variant
 int pick_pipe_envs(int W, bool f64, int sin) {
@@ -1057,11 +1264,6 @@ int pick_pipe_stages(const FeParams &p, bool f64) {
     return table <= ((size_t)48 << 20) ? 0 : kPipeSInStream;
 }
 
-// tuning overrides (sweeps only): FE_TILE_ENVS (multiple of 4), FE_TILE_THREADS (multiple of 32, <= 128)
-int env_override(const char *name) {
-    const char *v = getenv(name);
-    return v ? atoi(v) : 0;
-}
 
 template <typename OutT, bool kObserve>
 int launch(const FeParams &p, const FeSeries &s, const FeState &st, const float *actions, void *obs, void *rewards,
@@ -1089,6 +1291,31 @@ int launch(const FeParams &p, const FeSeries &s, const FeState &st, const float 
         kern<<<(unsigned)p.num_envs, kPortThreads, smem, stream>>>(p, s, st, k, actions, (OutT *)obs, (OutT *)rewards,
                                                                   dones, stats, step, step_dev, CH);
         return (int)cudaGetLastError();
+    }
+    static const int auto_scatter = env_override("FE_AUTO_SCATTER"); // sweeps: 1 = "auto" prefers scatter, -1 = never
+    const bool worth_persistent = p.num_envs >= (int64_t)4 * 148 * 32;
+    if (p.variant == FE_VARIANT_SCATTER || (p.variant == FE_VARIANT_AUTO && worth_persistent && auto_scatter > 0)) {
+        int TE, S, D;
+        if (pick_scatter(p.window, sizeof(OutT) == 8, &TE, &S, &D)) {
+            if ((uintptr_t)obs & 15) return FE_EALIGN;
+            auto kern = fe_scatter_kernel<OutT, kObserve>;
+            static bool configured[16] = {false};
+            static int num_sms[16] = {0};
+            const int dev = p.device & 15;
+            if (!configured[dev]) {
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+                if (e != cudaSuccess) return (int)e;
+                e = cudaDeviceGetAttribute(&num_sms[dev], cudaDevAttrMultiProcessorCount, p.device);
+                if (e != cudaSuccess) return (int)e;
+                configured[dev] = true;
+            }
+            const int64_t ntiles = (p.num_envs + TE - 1) / TE;
+            const unsigned blocks = (unsigned)(ntiles < num_sms[dev] ? ntiles : num_sms[dev]);
+            kern<<<blocks, kScThreads, scatter_smem_bytes<OutT>(TE, p.window, S), stream>>>(
+                p, s, st, k, actions, (OutT *)obs, (OutT *)rewards, dones, stats, step, step_dev, TE, S, D);
+            return (int)cudaGetLastError();
+        }
+        if (p.variant == FE_VARIANT_SCATTER) return FE_ESMEM;
     }
     static const int no_pipe = env_override("FE_NO_PIPE"); // sweeps: make "auto" fall through to the tile variant
     if (p.variant == FE_VARIANT_PIPE || (p.variant == FE_VARIANT_AUTO && !no_pipe)) {
@@ -1214,6 +1441,11 @@ const char *fe_step_kernel_name(const FeParams *p) {
     if (!p) return "";
     const bool f64 = p->out_f64 != 0;
     if (p->num_assets > 1 || p->variant == FE_VARIANT_PORTFOLIO) return f64 ? "fe_portfolio_kernel<double>" : "fe_portfolio_kernel<float>";
+    if (p->variant == FE_VARIANT_SCATTER ||
+        (p->variant == FE_VARIANT_AUTO && p->num_envs >= (int64_t)4 * 148 * 32 && env_override("FE_AUTO_SCATTER") > 0)) {
+        int TE, S, D;
+        if (pick_scatter(p->window, f64, &TE, &S, &D)) return f64 ? "fe_scatter_kernel<double>" : "fe_scatter_kernel<float>";
+    }
     if (p->variant == FE_VARIANT_PIPE || (p->variant == FE_VARIANT_AUTO && !env_override("FE_NO_PIPE"))) {
         const int ov = env_override("FE_PIPE_FLAVOUR");
         const int sin = ov == 1 ? 0 : ov == 2 ? kPipeSInStream : pick_pipe_stages(*p, f64);

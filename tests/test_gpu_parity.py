@@ -30,11 +30,14 @@ def _env(series, **kw):
 @pytest.mark.parametrize("dtype,variant", [(torch.float32, "auto"), (torch.float64, "auto"), (torch.float32, "direct"),
                                            (torch.float64, "direct"), (torch.float32, "portfolio"),
                                            (torch.float64, "portfolio"), (torch.float32, "pipe"),
-                                           (torch.float64, "pipe")])
+                                           (torch.float64, "pipe"), (torch.float32, "scatter"),
+                                           (torch.float64, "scatter")])
 def test_cuda_replays_reference_trace(name, dtype, variant):
     z = load_trace(name)
     if variant == "pipe" and _lib_mod().lib().fe_pipe_envs(int(z["window"]), int(dtype == torch.float64), 0) == 0:
         pytest.skip("window too large for the pipe variant's rings")
+    if variant == "scatter" and int(z["window"]) * 5 * (8 if dtype == torch.float64 else 4) * 4 * 4 > 220 * 1024:
+        pytest.skip("window too large for the scatter variant's ring (4 stages of 4 envs)")
     series = stage_trace_series(z, dtype)
     N = len(z["seg_init"])
     env = _env(series, num_envs=N, evaluate=bool(z["evaluate"]), seed=int(z["seed"]), obs_dtype=dtype, variant=variant)
@@ -456,9 +459,10 @@ def test_flat_obs_and_es_env_args():
     assert o0.shape == (500, W * 5) and int(b._ptr.abs().sum()) == 0 and float(b._cash.min()) == 10000.0
 
 
+@pytest.mark.parametrize("variant", ["pipe", "scatter"])
 @pytest.mark.parametrize("W,N,dtype", [(60, 1024, torch.float32), (60, 5003, torch.float32), (60, 4099, torch.float64),
                                        (8, 70001, torch.float32), (128, 3000, torch.float32), (3, 999, torch.float32)])
-def test_pipe_variant_vs_oracle(W, N, dtype):
+def test_pipe_variant_vs_oracle(W, N, dtype, variant):
     """The persistent warp-specialised pipeline: many tiles per block (N >> 148 * 32), ragged last tile, small and
     larger windows (32/16/8-env tiles), both dtypes, resets with redraws — exact against the oracle."""
     from oracle import oracle as orc
@@ -467,7 +471,7 @@ def test_pipe_variant_vs_oracle(W, N, dtype):
     prices, seg_start, seg_len = _c1_series(W, days=80, bars=37, sigma=0.05, seed=W * 7 + N)
     series = loader.stage_series(prices, seg_start, seg_len, W, "cuda:0", dtype, keep_logret64=True)
     fs = orc.series_from_prices(prices, seg_start, seg_len, W, logret=series.logret64.cpu().numpy())
-    env = _env(series, num_envs=N, seed=4, random_reset="all", random_offset=True, obs_dtype=dtype, variant="pipe",
+    env = _env(series, num_envs=N, seed=4, random_reset="all", random_offset=True, obs_dtype=dtype, variant=variant,
                track_stats=True)
     ref = orc.OracleEnv(fs, num_envs=N, seed=4, reset_mode=2, random_offset=True, out_f64=dtype == torch.float64)
     n_done = _lockstep(env, ref, 60, np.random.default_rng(N), obs_every=4)
