@@ -214,6 +214,7 @@ def main():
     ap.add_argument("--window", type=int, default=None, help="default 60; c3: 128")
     ap.add_argument("--variant", default="auto", choices=["auto", "tile", "direct", "pipe", "scatter"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to its GPU's NUMA-local CPUs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     args.envs = args.envs or WORKLOAD_DEFAULTS[args.workload][0]
@@ -231,6 +232,9 @@ def main():
     from finenvs_b200 import parallel as par
     from finenvs_b200.data import loader
 
+    prev_affinity = None
+    if not args.no_numa_bind:   # before the CUDA context and any pinned allocation exist
+        prev_affinity = par.bind_to_gpu_numa(int(os.environ.get("LOCAL_RANK", "0")))
     rank, world, local_rank = par.init_distributed("nccl")
     torch.cuda.set_device(local_rank)
     dev = f"cuda:{local_rank}"
@@ -333,6 +337,9 @@ def main():
         "clocks": sampler.summary(),
         "episodes_finished_last_step": n_done,
     }
+    line["config"]["numa_bound_cpus"] = len(os.sched_getaffinity(0)) if prev_affinity is not None else None
+    if prev_affinity is not None:
+        os.sched_setaffinity(0, prev_affinity)   # the CPU baseline uses every host core
     if world == 1 and not args.no_cpu_baseline:
         sample = min(N, 262144 // A // (2 if A > 1 else 1))
         v, sps, threads, n = cpu_oracle_throughput(W, args.workload, sample, 10_000, 3, 12.0)

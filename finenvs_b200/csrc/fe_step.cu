@@ -48,24 +48,9 @@ __device__ __forceinline__ double relu64(double x) { return x < 0.0 ? 0.0 : x; }
 struct Consts {
     float ms, scale, cf, imrf, SBf;
     double c, imr, mmr1, SB;
-    // fe_step_host with pinned host buffers (HostIo): second destination of rewards / dones in mapped host memory, and
-    // the arrival flag of the chunked action upload (actions of env i are in HBM once *h2d_flag - h2d_base > i >> h2d_shift)
+    // optional second destination of rewards / dones (fe_step_host's zero-copy mode: mapped pinned host memory)
     void *rewards_mirror;
     int32_t *dones_mirror;
-    const uint32_t *h2d_flag;
-    uint32_t h2d_base;
-    int32_t h2d_shift;
-    int64_t h2d_head;          // envs [0, h2d_head) read their action straight from mapped host memory (actions_head)
-    const float *actions_head;
-};
-struct HostIo {
-    void *rewards_mirror;
-    int32_t *dones_mirror;
-    const uint32_t *h2d_flag;
-    uint32_t h2d_base;
-    int32_t h2d_shift;
-    int64_t h2d_head;
-    const float *actions_head;
 };
 
 Consts make_consts(const FeParams &p) {
@@ -81,11 +66,6 @@ Consts make_consts(const FeParams &p) {
     k.SB = p.starting_balance;
     k.rewards_mirror = nullptr;
     k.dones_mirror = nullptr;
-    k.h2d_flag = nullptr;
-    k.h2d_base = 0;
-    k.h2d_shift = 0;
-    k.h2d_head = 0;
-    k.actions_head = nullptr;
     return k;
 }
 
@@ -126,33 +106,16 @@ __device__ __forceinline__ EnvResult env_observe(const FeParams &p, const FeSeri
     return r;
 }
 
-// The action of env `env` (element idx of the actions array).  Under fe_step_host's pinned mode the first h2d_head envs
-// read theirs straight from mapped host memory (no wait for any copy to start), the others wait for their chunk of the
-// copy engine's upload: the arrival counter is written by a copy queued behind the chunk's.  `seen` caches the last
-// counter value this thread read, so once a chunk has arrived (the whole upload is much shorter than the kernel) no
-// env of it polls again.  Polling is a volatile load (no acquire: an acquire at system scope invalidates the SM's L1
-// on every poll); the action itself is read with ld.global.cg, i.e. from L2, where the copy engine's writes land, and
-// is issued only after the poll loop's exit branch has resolved.
-__device__ __forceinline__ float load_action(const Consts &k, const float *__restrict__ actions, int64_t idx, int64_t env,
-                                             uint32_t &seen) {
-    if (k.h2d_flag) {
-        if (env < k.h2d_head) return __ldcg(k.actions_head + idx);
-        const uint32_t need = k.h2d_base + (uint32_t)((env - k.h2d_head) >> k.h2d_shift) + 1u;
-        while ((int32_t)(seen - need) < 0) {
-            asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(seen) : "l"(k.h2d_flag) : "memory");
-            if ((int32_t)(seen - need) < 0) __nanosleep(200);
-        }
-    }
-    return __ldcg(actions + idx);
-}
-
 template <typename OutT>
 __device__ __forceinline__ EnvResult env_step(const FeParams &p, const FeSeries &s, const FeState &st,
                                               const Consts &k, int64_t i, const float *__restrict__ actions,
                                               OutT *__restrict__ rewards, int32_t *__restrict__ dones,
-                                              bool track, uint64_t step, uint32_t &seen) {
+                                              bool track, uint64_t step) {
     EnvResult res;
     const int W = p.window;
+    // :298-302 action -> integer share delta (round half to even, then clamp)
+    float d = rintf(fmul(__ldg(actions + i), k.scale));
+    d = d < -k.ms ? -k.ms : (d > k.ms ? k.ms : d);
     // :281-282 advance time
     int32_t seg = st.seg[i];
     int32_t ptr = st.ptr[i] + 1;
@@ -167,9 +130,6 @@ __device__ __forceinline__ EnvResult env_step(const FeParams &p, const FeSeries 
     float sht = st.short_sh[i];
     double margin = st.margin[i];
     float comm = 0.0f; // :305
-    // :298-302 action -> integer share delta (round half to even, then clamp); read last: it may still be in flight
-    float d = rintf(fmul(load_action(k, actions, i, i, seen), k.scale));
-    d = d < -k.ms ? -k.ms : (d > k.ms ? k.ms : d);
     // :344-351
     float pos = d < 0.0f ? 0.0f : d;
     float neg = d > 0.0f ? 0.0f : d;
@@ -340,7 +300,6 @@ fe_tile_kernel(const FeParams p, const FeSeries s, const FeState st, const Const
     const bool active = tid < nvalid;
     EnvResult r;
     r.done = 0; r.newly_terminated = 0; r.fin_return = 0.0; r.fin_len = 0;
-    uint32_t seen = k.h2d_base;
     if (active) {
         const int64_t i = env0 + tid;
         // window start is known before any arithmetic: launch the copy first
@@ -349,7 +308,7 @@ fe_tile_kernel(const FeParams p, const FeSeries s, const FeState st, const Const
         bulk_load(smem_u32(in_tile + (size_t)tid * win_bytes),
                   reinterpret_cast<const unsigned char *>(s.logret) + (size_t)row0 * row_bytes, win_bytes, bar);
         if (kObserve) r = env_observe(p, s, st, k, i);
-        else r = env_step<OutT>(p, s, st, k, i, actions, rewards, dones, stats != nullptr, step, seen);
+        else r = env_step<OutT>(p, s, st, k, i, actions, rewards, dones, stats != nullptr, step);
         pf[tid] = (OutT)r.posfeat;
     }
     if (!kObserve && tid < ((nvalid + 31) & ~31)) accumulate_stats(stats, r, active);
@@ -497,7 +456,6 @@ fe_pipe_kernel(const FeParams p, const FeSeries s, const FeState st, const Const
 
     if (warp < kPipeBook) {
         // ------------------------------------------------------------------ bookkeepers
-        uint32_t seen = k.h2d_base;
         for (int t = warp; t < ntiles; t += kPipeBook) {
             const int q = t % kPipeQ;
             mbar_wait(desc_free(q), ((t / kPipeQ) & 1) ^ 1); // first lap passes immediately
@@ -509,7 +467,7 @@ fe_pipe_kernel(const FeParams p, const FeSeries s, const FeState st, const Const
             if (active) {
                 const int64_t i = env0 + lane;
                 if (kObserve) r = env_observe(p, s, st, k, i);
-                else r = env_step<OutT>(p, s, st, k, i, actions, rewards, dones, stats != nullptr, step, seen);
+                else r = env_step<OutT>(p, s, st, k, i, actions, rewards, dones, stats != nullptr, step);
                 d_row0[q * TE + lane] = r.row0;
                 reinterpret_cast<OutT *>(d_pf + q * TE)[lane] = (OutT)r.posfeat;
             }
@@ -701,7 +659,6 @@ fe_scatter_kernel(const FeParams p, const FeSeries s, const FeState st, const Co
 
     if (warp < kScBook) {
         // ------------------------------------------------------------------ bookkeepers
-        uint32_t seen = k.h2d_base;
         for (int t = warp; t < ntiles; t += kScBook) {
             const int q = t % kScQ;
             mbar_wait(desc_free(q), ((t / kScQ) & 1) ^ 1); // first lap passes immediately
@@ -713,7 +670,7 @@ fe_scatter_kernel(const FeParams p, const FeSeries s, const FeState st, const Co
             if (active) {
                 const int64_t i = env0 + lane;
                 if (kObserve) r = env_observe(p, s, st, k, i);
-                else r = env_step<OutT>(p, s, st, k, i, actions, rewards, dones, stats != nullptr, step, seen);
+                else r = env_step<OutT>(p, s, st, k, i, actions, rewards, dones, stats != nullptr, step);
                 d_row0[q * TE + lane] = r.row0;
                 reinterpret_cast<OutT *>(d_pf + q * TE)[lane] = (OutT)r.posfeat;
             }
@@ -821,11 +778,10 @@ fe_direct_kernel(const FeParams p, const FeSeries s, const FeState st, const Con
     const bool active = tid < nvalid;
     EnvResult r;
     r.done = 0; r.newly_terminated = 0; r.fin_return = 0.0; r.fin_len = 0; r.row0 = 0; r.posfeat = 0.0;
-    uint32_t seen = k.h2d_base;
     if (active) {
         const int64_t i = env0 + tid;
         if (kObserve) r = env_observe(p, s, st, k, i);
-        else r = env_step<OutT>(p, s, st, k, i, actions, rewards, dones, stats != nullptr, step, seen);
+        else r = env_step<OutT>(p, s, st, k, i, actions, rewards, dones, stats != nullptr, step);
     }
     sh_row0[tid] = r.row0;
     sh_pf[tid] = (OutT)r.posfeat;
@@ -861,10 +817,9 @@ fe_lazy_kernel(const FeParams p, const FeSeries s, const FeState st, const Const
     const bool active = i < p.num_envs;
     EnvResult r;
     r.done = 0; r.newly_terminated = 0; r.fin_return = 0.0; r.fin_len = 0; r.row0 = 0; r.posfeat = 0.0;
-    uint32_t seen = k.h2d_base;
     if (active) {
         if (kObserve) r = env_observe(p, s, st, k, i);
-        else r = env_step<OutT>(p, s, st, k, i, actions, rewards, dones, stats != nullptr, step, seen);
+        else r = env_step<OutT>(p, s, st, k, i, actions, rewards, dones, stats != nullptr, step);
         row0_out[i] = r.row0;
         pf_out[i] = (OutT)r.posfeat;
     }
@@ -929,13 +884,12 @@ __device__ __forceinline__ void portfolio_step(const FeParams &p, const FeSeries
     double *xa = scratch, *xb = scratch + 32, *xc = scratch + 64; // __syncwarp() orders the exchanges
     double O = 1.0, H = 1.0, L = 1.0, C = 1.0, margin = 0.0;
     float lng = 0.0f, sht = 0.0f, d = 0.0f;
-    uint32_t seen = k.h2d_base;
     if (act) {
         const double2 *px = reinterpret_cast<const double2 *>(s.prices + ((row0 + W - 1) * A + lane) * 4);
         const double2 oh = __ldg(px), lc = __ldg(px + 1);
         O = oh.x; H = oh.y; L = lc.x; C = lc.y;
         lng = st.long_sh[ia]; sht = st.short_sh[ia]; margin = st.margin[ia];
-        d = rintf(fmul(load_action(k, actions, ia, i, seen), k.scale));            // :298-302
+        d = rintf(fmul(__ldg(actions + ia), k.scale));                       // :298-302
         d = d < -k.ms ? -k.ms : (d > k.ms ? k.ms : d);
     }
     float cash = st.cash[i];
@@ -1314,13 +1268,10 @@ int pick_pipe_stages(const FeParams &p, bool f64) {
 template <typename OutT, bool kObserve>
 int launch(const FeParams &p, const FeSeries &s, const FeState &st, const float *actions, void *obs, void *rewards,
            int32_t *dones, FeStats *stats, uint64_t step, cudaStream_t stream, const uint64_t *step_dev = nullptr,
-           const HostIo *hio = nullptr) {
+           void *rewards_mirror = nullptr, int32_t *dones_mirror = nullptr) {
     Consts k = make_consts(p);
-    if (hio) {
-        k.rewards_mirror = hio->rewards_mirror; k.dones_mirror = hio->dones_mirror;
-        k.h2d_flag = hio->h2d_flag; k.h2d_base = hio->h2d_base; k.h2d_shift = hio->h2d_shift;
-        k.h2d_head = hio->h2d_head; k.actions_head = hio->actions_head;
-    }
+    k.rewards_mirror = rewards_mirror;
+    k.dones_mirror = dones_mirror;
     if (p.num_assets > 1 || p.variant == FE_VARIANT_PORTFOLIO) {
         if ((uintptr_t)obs & 15) return FE_EALIGN;
         const int P = p.window * p.num_assets;
@@ -1442,14 +1393,9 @@ int set_device(int device) {
 
 // side streams of fe_step_host (created once per device, never destroyed: they live as long as the process)
 constexpr int kHostStreams = 3;
-constexpr int kFlagRing = 64;
 struct HostPipe {
     cudaStream_t s[kHostStreams];
     cudaEvent_t start, done[kHostStreams];
-    uint32_t *flag_dev;   // arrival counter of the chunked action upload (device memory, 4 bytes used)
-    uint32_t *flag_vals;  // pinned host ring of the values the copy engine writes into it
-    uint32_t flag_base;   // value the counter has reached (host mirror)
-    uint32_t flag_slot;
     bool ready;
 };
 HostPipe *host_pipe(int device) {
@@ -1461,11 +1407,6 @@ HostPipe *host_pipe(int device) {
             if (cudaEventCreateWithFlags(&hp->done[k], cudaEventDisableTiming) != cudaSuccess) return nullptr;
         }
         if (cudaEventCreateWithFlags(&hp->start, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        if (cudaMalloc(&hp->flag_dev, 256) != cudaSuccess) return nullptr;
-        if (cudaMemset(hp->flag_dev, 0, 256) != cudaSuccess) return nullptr;
-        if (cudaHostAlloc(&hp->flag_vals, kFlagRing * sizeof(uint32_t), cudaHostAllocDefault) != cudaSuccess) return nullptr;
-        hp->flag_base = 0;
-        hp->flag_slot = 0;
         hp->ready = true;
     }
     return hp;
@@ -1643,18 +1584,16 @@ int fe_step_host(const FeParams *p, const FeSeries *s, const FeState *st, const 
     const int64_t n = p->num_envs;
     const int A = p->num_assets;
     const size_t osz = p->out_f64 ? 8 : 4;
-    // Pinned mode: when all three host buffers are pinned (mapped into the device's address space)
-    //   * rewards / dones: the step kernel writes them to host memory itself (posted PCIe writes spread over the whole
-    //     kernel; no download after it).  rewards_dev / dones_dev are written as well (device-side consumers);
-    //   * actions: the first 256 KB are read by the kernel straight from host memory; the rest is uploaded by the copy
-    //     engine in up to 8 chunks on a side stream, each followed by a 4-byte copy that bumps an arrival counter in
-    //     HBM; the ONE step kernel is launched first and an env waits for its chunk's counter value before reading
-    //     its action (load_action).  The upload (4 MB per Mi envs) is far shorter than the kernel and starts while
-    //     the kernel works on the directly-read head, so none of it is exposed.  FE_HOST_ZEROCOPY_READ=1 (experiments) lets the
-    //     kernel read the actions straight from host memory instead: as fast on one GPU, but latency-bound when
-    //     eight GPUs hit the host at once (measured 0.68 ms vs 0.31 ms per step).
+    // Zero-copy mode: when all three host buffers are pinned (mapped into the device's address space), the step
+    // kernel reads the actions from them and writes rewards / dones to them directly over PCIe — 12 bytes per env
+    // spread over the whole kernel, no copy-engine hop, no head (upload) or tail (download) outside the kernel.
+    // rewards_dev / dones_dev are written as well (device-side consumers); actions_dev is left untouched.
+    // (Tried instead: copy-engine upload of the actions in chunks behind the already running kernel, each chunk
+    // followed by a 4-byte copy bumping an arrival counter the envs poll.  Same speed on one GPU (0.317 ms per
+    // 1 Mi-env step) and on eight (0.67 vs 0.68 ms: with 8 ranks the host side of PCIe, not the read latency, is the
+    // limit), more machinery, and a kernel that waits for copies queued after it deadlocks under anything that
+    // serialises launches (ncu, CUDA_LAUNCH_BLOCKING=1) — dropped.)
     static const int no_zc = env_override("FE_HOST_NO_ZEROCOPY");
-    static const int zc_read = env_override("FE_HOST_ZEROCOPY_READ");
     if (!no_zc) {
         cudaPointerAttributes aa, ar, ad;
         const bool ok = cudaPointerGetAttributes(&aa, actions_host) == cudaSuccess && aa.type == cudaMemoryTypeHost &&
@@ -1662,51 +1601,15 @@ int fe_step_host(const FeParams *p, const FeSeries *s, const FeState *st, const 
                         ar.type == cudaMemoryTypeHost && ar.devicePointer &&
                         cudaPointerGetAttributes(&ad, dones_host) == cudaSuccess && ad.type == cudaMemoryTypeHost &&
                         ad.devicePointer;
-        (void)cudaGetLastError(); // an unregistered pointer may leave an error behind
+        (void)cudaGetLastError(); // an unregistered pointer leaves a sticky-free error on old drivers
         if (ok) {
-            HostIo hio = {ar.devicePointer, (int32_t *)ad.devicePointer, nullptr, 0u, 0, 0, nullptr};
             const float *a = (const float *)aa.devicePointer;
-            HostPipe *hpp = nullptr;
-            int64_t head = 0;
-            int shift = 14, nchunks = 0; // chunks of 2^shift envs: at least 16 Ki envs, at most 8 chunks
-            if (!zc_read) {
-                hpp = host_pipe(p->device);
-                if (!hpp) return (int)cudaGetLastError();
-                head = (int64_t)65536 / A; // 256 KB of actions: ~20 us of kernel time, enough for the upload to get going
-                if (head > n) head = n;
-                const int64_t rest = n - head;
-                while (((rest + ((int64_t)1 << shift) - 1) >> shift) > 8) ++shift;
-                nchunks = (int)((rest + ((int64_t)1 << shift) - 1) >> shift);
-                hio.h2d_flag = hpp->flag_dev;
-                hio.h2d_base = hpp->flag_base;
-                hio.h2d_shift = shift;
-                hio.h2d_head = head;
-                hio.actions_head = a;
-                a = actions_dev;
-            }
-            // the kernel goes first: enqueueing the copies costs the host a few us each, and the first tiles do not
-            // need them
             rc = p->out_f64 ? launch<double, false>(*p, *s, *st, a, obs_dev, rewards_dev, dones_dev, stats_dev, step_counter, q,
-                                                    nullptr, &hio)
+                                                    nullptr, ar.devicePointer, (int32_t *)ad.devicePointer)
                             : launch<float, false>(*p, *s, *st, a, obs_dev, rewards_dev, dones_dev, stats_dev, step_counter, q,
-                                                   nullptr, &hio);
+                                                   nullptr, ar.devicePointer, (int32_t *)ad.devicePointer);
             if (rc) return rc;
-            cudaError_t e = cudaSuccess;
-            for (int c = 0; c < nchunks; ++c) {
-                const int64_t off = head + ((int64_t)c << shift);
-                const int64_t cnt = off + ((int64_t)1 << shift) <= n ? ((int64_t)1 << shift) : n - off;
-                uint32_t *slot = hpp->flag_vals + (hpp->flag_slot++ % kFlagRing);
-                *slot = hpp->flag_base + (uint32_t)c + 1u;
-                if (e == cudaSuccess)
-                    e = cudaMemcpyAsync(actions_dev + off * A, actions_host + off * A, (size_t)cnt * A * sizeof(float),
-                                        cudaMemcpyHostToDevice, hpp->s[0]);
-                // the counter is bumped even if a copy could not be queued, so that the running kernel always ends
-                cudaError_t e2 = cudaMemcpyAsync(hpp->flag_dev, slot, sizeof(uint32_t), cudaMemcpyHostToDevice, hpp->s[0]);
-                if (e == cudaSuccess) e = e2;
-            }
-            if (hpp) hpp->flag_base += (uint32_t)nchunks;
-            const cudaError_t es = cudaStreamSynchronize(q);
-            return (int)(e != cudaSuccess ? e : es);
+            return (int)cudaStreamSynchronize(q);
         }
     }
     static const int ov_chunks = env_override("FE_HOST_CHUNKS");

@@ -37,6 +37,30 @@ def init_distributed(backend: Optional[str] = None) -> Tuple[int, int, int]:
     return rank, world, local_rank
 
 
+def bind_to_gpu_numa(device_index: int):
+    """Pin this process to the CPUs NVML reports as local to GPU `device_index` (its NUMA node), so that the pinned host
+    buffers it allocates afterwards (first touch) and its driver threads sit next to the GPU's PCIe root.  One process
+    per GPU makes this the natural placement; without it every rank's buffers tend to land on one socket and the
+    host-buffer step (fe_step_host) of 8 ranks shares that socket's memory and inter-socket links.
+    Returns the previous affinity set (hand it to os.sched_setaffinity(0, ...) to undo) or None if nothing was done."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        prev = os.sched_getaffinity(0)
+        cpus &= prev
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return prev
+    except Exception:
+        return None
+
+
 def shard_bounds(total_envs: int, rank: int, world_size: int) -> Tuple[int, int]:
     """Contiguous block of global env ids owned by `rank`: (first id, count).  The remainder goes to
     the lowest ranks, so the global last env (the reference's evaluation env) is on the last rank."""

@@ -9,10 +9,9 @@
  *
  * Conventions
  *   - plain pointers + sizes, no torch / C++ types; every `*_dev` / struct pointer member is a DEVICE
- *     pointer owned by the caller (the library allocates no per-env or per-call memory and frees nothing of the caller's;
- *     fe_step_host alone keeps a few streams, events and a 256-byte counter per device);
+ *     pointer owned by the caller (the library allocates nothing persistent and frees nothing);
  *   - `stream` is a cudaStream_t (CUstream) passed as void*; calls only enqueue work and never
- *     synchronise, except fe_step_host which returns after its results are in host memory;
+ *     synchronise, except fe_step_host which returns after its device->host copies completed;
  *   - return 0 on success, a negative FE_E* code for a rejected argument, or a positive cudaError_t;
  *   - no exceptions cross the boundary; there is NO CPU fallback: without a CUDA device every compute
  *     entry point returns a cudaError.
@@ -152,13 +151,11 @@ int fe_materialize(const FeParams *p, const FeSeries *s, const int64_t *obs_row0
                    void *obs_dev, void *stream);
 
 /* Same step driven from HOST buffers (the call a non-torch embedder makes).  When actions_host, rewards_host and
- * dones_host are all pinned (cudaHostAlloc / cudaHostRegister): the actions are uploaded by the copy engine in chunks
- * on a side stream while the ONE step kernel already runs (an env waits for its chunk's arrival counter), and the
- * kernel writes rewards / dones straight into host memory over PCIe — no separate download.  Otherwise the envs are
- * cut into chunks whose upload, kernel and download are pipelined over three streams.  Either way the call returns
- * after the results are in rewards_host / dones_host; rewards_dev / dones_dev hold the same values; the observation
- * stays in HBM (obs_dev) for the policy.  actions_dev is scratch (N*A floats).  The library keeps a few streams,
- * events and a 256-byte device counter per device for this call (created on first use, never freed). */
+ * dones_host are all pinned (cudaHostAlloc / cudaHostRegister), the step kernel itself reads the actions from and
+ * writes rewards / dones to host memory over PCIe (zero-copy: no separate upload or download); otherwise the envs
+ * are cut into chunks whose upload, kernel and download are pipelined over three streams.  Either way the call
+ * returns after the results are in rewards_host / dones_host; rewards_dev / dones_dev hold the same values; the
+ * observation stays in HBM (obs_dev) for the policy.  actions_dev is scratch (N*A floats). */
 int fe_step_host(const FeParams *p, const FeSeries *s, const FeState *st, const float *actions_host,
                  float *actions_dev, void *obs_dev, void *rewards_dev, int32_t *dones_dev, void *rewards_host,
                  int32_t *dones_host, FeStats *stats_dev, uint64_t step_counter, void *stream);
