@@ -5,7 +5,7 @@
 // the layout in which the env writes one (N, ...) slab per step.  One thread per env walks t = T-1 .. 0;
 // every load and store is coalesced over the env dimension; the loads of the next kUnroll time steps do not
 // depend on the running value, so they are issued ahead of the dependent multiply-add chain.
-// Arithmetic follows the reference dtype for dtype (DESIGN.md §10): f32 products/sums for f32
+// Arithmetic follows the reference dtype for dtype (DESIGN.md §4.6): f32 products/sums for f32
 // rewards; for f64 rewards the running value is f64 after the first iteration and each stored return is
 // rounded once.  No FMA contraction (explicit __*_rn intrinsics; the TU is also built with -fmad=false).
 #include "finenvs_b200.h"

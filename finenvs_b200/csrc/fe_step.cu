@@ -845,7 +845,7 @@ fe_materialize_kernel(const int64_t N, const int W, const OutT *__restrict__ log
 
 // ------------------------------------------------------------------------------------------
 // portfolio variant (A > 1 assets, one cash account): EXTENSION, the reference is single-asset (:223).
-// Semantics (DESIGN.md §4.4): the reference's phases in the reference's order; inside a phase the
+// Semantics (DESIGN.md §3, §4.4): the reference's phases in the reference's order; inside a phase the
 // assets are visited in index order, each applying the A = 1 arithmetic to (cash, asset a).  One block
 // per env; warp 0 does the bookkeeping with lane = asset: every per-asset quantity is lane-local, only
 // the f32 cash chain is serial, walked with warp shuffles (all lanes keep an identical copy of cash).

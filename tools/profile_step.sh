@@ -3,8 +3,8 @@
 # usage: tools/profile_step.sh <workload> <tag> [kernel regex]
 WL=$1; TAG=$2; KRE=${3:-fe_pipe}
 CMD="python bench.py --workload $WL --steps 6 --warmup 3 --no-cpu-baseline"
-$CMD > gpurun_out/plain_${TAG}.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_${TAG}.csv $CMD > gpurun_out/ncu_l_${TAG}.log 2>&1
-$CMD > gpurun_out/plain_${TAG}.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:$KRE -s 4 -c 2 -f -o gpurun_out/prof_${TAG} $CMD > gpurun_out/ncu_f_${TAG}.log 2>&1
+timeout 120 $CMD > gpurun_out/plain_${TAG}.log 2>&1 &&
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_${TAG}.csv $CMD > gpurun_out/ncu_l_${TAG}.log 2>&1
+timeout 120 $CMD > gpurun_out/plain_${TAG}.log 2>&1 &&
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:$KRE -s 4 -c 2 -f -o gpurun_out/prof_${TAG} $CMD > gpurun_out/ncu_f_${TAG}.log 2>&1
 tail -2 gpurun_out/ncu_f_${TAG}.log
