@@ -178,8 +178,9 @@ class TimeSeriesEnv(BaseObject):
                       population (multi-GPU); draws are keyed by global id, so results do not
                       depend on the sharding.
         track_stats   accumulate episode count / return / length on the device (stats()).
-        variant       "auto" | "pipe" | "tile" | "direct" | "portfolio" kernel variant (auto: pipe for populations
-                      of >= 18 944 envs, else tile; direct when the window does not fit in shared memory).
+        variant       "auto" | "pipe" | "tile" | "direct" | "scatter" | "portfolio" kernel variant (auto: pipe for
+                      populations of >= 18 944 envs with windows of >= 24 rows, else tile; direct when the window does
+                      not fit in shared memory; portfolio whenever the series has more than one asset).
         flat_obs      return observations as (N, W*num_obs) — the 2-D input the ES agent's ParallelMLP needs
                       (parallel_mlp.py:98-103); same memory, only the shape differs.
         num_eval_envs reported in get_env_args() for the ES agent (evo_agent.py:53); the last
