@@ -539,6 +539,205 @@ fe_es_forward_fast_kernel(const EsLayout lay, const FastShape fs, const float *_
 }
 
 // ------------------------------------------------------------------------------------------
+// forward, streaming path: any tanh MLP whose layers have <= 319 inputs (e.g. the reference's default 256-256 hidden
+// layers, evo_agent.py:16).  The generic kernel above reads eps and theta with plain loads, one 8-output chunk of one
+// pair at a time: 5.7 ms per step for 64 Ki envs x a 300-256-256-1 policy (9.5 GB of eps, 1.67 TB/s).  Here a warp
+// owns U pairs at a time and walks the network chunk by chunk (8 outputs x (in+1) rows):
+//   * the chunk's theta rows of a lane (<= 10 rows x 8 outputs) are loaded ONCE into registers and reused for the
+//     warp's U pairs (theta traffic from L2 / L1 drops by U and leaves the shared-memory pipe to eps and x);
+//   * a pair's eps chunk ((in+1) x 16 bytes, contiguous in the packed layout) arrives by one bulk async copy into the
+//     warp's ring, issued kStStages-1 (pair, chunk) steps ahead, completing on the stage's mbarrier;
+//   * activations of the U pairs live in shared memory as (x+, x-) float2 per input.
+// ------------------------------------------------------------------------------------------
+constexpr int kStWarps = 8;
+constexpr int kStThreads = kStWarps * 32;
+constexpr int kStStages = 3;
+constexpr int kStRows = 10;   // rows per lane: in + 1 <= 320
+constexpr int kStMaxU = 4;
+
+struct StreamShape {
+    int U;            // pairs per warp per group
+    int stage_bytes;  // largest eps chunk, rounded to 128
+    int strideA, strideB; // float2 entries per pair in the two activation buffers (inputs of even / odd layers)
+    int chunks[FE_ES_MAX_LAYERS + 1]; // cumulative chunk counts: chunks[l] = chunks of layers < l
+};
+__host__ __device__ inline size_t stream_smem_bytes(const StreamShape &f) {
+    return 256 + (size_t)kStWarps * ((size_t)kStStages * f.stage_bytes + (size_t)f.U * (f.strideA + f.strideB) * 8);
+}
+
+template <bool kLazy>
+__global__ void __launch_bounds__(kStThreads, 1)
+fe_es_forward_stream_kernel(const EsLayout lay, const StreamShape fs, const float *__restrict__ theta,
+                            const __half *__restrict__ eps, const float sigma, const int64_t num_pairs, const int64_t num_eval,
+                            const float *__restrict__ obs, const float *__restrict__ logret, const int64_t *__restrict__ row0,
+                            const float *__restrict__ posfeat, const int W, const float noise_std, const uint64_t seed,
+                            const uint64_t step, const int64_t env_id_base, float *__restrict__ actions) {
+    extern __shared__ __align__(128) unsigned char ssm[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t P = lay.off[lay.L];
+    const int U = fs.U, I = lay.in[0], OL = lay.out[lay.L - 1];
+    const size_t warp_bytes = (size_t)kStStages * fs.stage_bytes + (size_t)U * (fs.strideA + fs.strideB) * 8;
+    unsigned char *ring = ssm + 256 + (size_t)warp * warp_bytes;
+    float2 *actA = reinterpret_cast<float2 *>(ring + (size_t)kStStages * fs.stage_bytes); // [U][strideA]
+    float2 *actB = actA + (size_t)U * fs.strideA;                                         // [U][strideB]
+    const uint32_t bar0 = smem_u32(ssm) + (uint32_t)warp * kStStages * 8u;
+    if (lane == 0)
+        for (int s = 0; s < kStStages; ++s) mbar_init(bar0 + 8u * s, 1);
+    mbar_fence_init();
+    __syncthreads();
+
+    const int64_t units = num_pairs + num_eval;
+    const int total_chunks = fs.chunks[lay.L];
+    const int m = lane >> 1, om = m & 7;
+    auto env_of = [&](int64_t u, int sgn) -> int64_t { // :121-136 positives first, negatives second, eval envs last
+        if (u >= num_pairs) return 2 * num_pairs + (u - num_pairs);
+        return sgn ? u + num_pairs : u;
+    };
+    uint32_t gi = 0, gc = 0; // steps issued / consumed by this warp since the kernel started (stage = g % S)
+    for (int64_t first = ((int64_t)blockIdx.x * kStWarps + warp) * U; first < units; first += (int64_t)gridDim.x * kStWarps * U) {
+        const int nu = (int)(units - first < U ? units - first : U);
+        const int nsteps = nu * total_chunks;
+        // step s of this group = chunk s / nu (layer l, chunk c) of pair first + s % nu
+        auto issue = [&](int sidx) {
+            if (sidx >= nsteps) return;
+            const int cc = sidx / nu, u = sidx - cc * nu;
+            int l = 0;
+            while (l + 1 < lay.L && cc >= fs.chunks[l + 1]) ++l;
+            const int c = cc - fs.chunks[l], in1 = lay.in[l] + 1;
+            const int64_t unit = first + u;
+            const uint32_t bar = bar0 + 8u * (gi % kStStages);
+            unsigned char *stage = ring + (size_t)(gi % kStStages) * fs.stage_bytes;
+            ++gi;
+            if (lane == 0) {
+                if (unit < num_pairs) {
+                    mbar_arrive_expect_tx(bar, (uint32_t)in1 * 16u);
+                    bulk_load(smem_u32(stage), eps + unit * P + lay.off[l] + (int64_t)c * in1 * 8, (uint32_t)in1 * 16u, bar);
+                } else {
+                    mbar_arrive(bar); // evaluation env: no perturbation to fetch
+                }
+            }
+        };
+        for (int sidx = 0; sidx < kStStages - 1; ++sidx) issue(sidx);
+        // ---- inputs of layer 0: actA[u][j] = (x of the + env, x of the - env), entry I = the constant 1 of the bias row
+        for (int u = 0; u < nu; ++u) {
+            const int64_t unit = first + u, e0 = env_of(unit, 0), e1 = env_of(unit, 1);
+            float2 *x = actA + (size_t)u * fs.strideA;
+            if (kLazy) {
+                const float4 *s0 = reinterpret_cast<const float4 *>(logret) + row0[e0];
+                const float4 *s1 = reinterpret_cast<const float4 *>(logret) + row0[e1];
+                const float p0 = posfeat[e0], p1 = posfeat[e1];
+                for (int r = lane; r < W; r += 32) {
+                    const float4 a = __ldg(s0 + r), b = __ldg(s1 + r);
+                    x[r * 5 + 0] = make_float2(a.x, b.x); x[r * 5 + 1] = make_float2(a.y, b.y);
+                    x[r * 5 + 2] = make_float2(a.z, b.z); x[r * 5 + 3] = make_float2(a.w, b.w);
+                    x[r * 5 + 4] = make_float2(p0, p1);
+                }
+            } else {
+                for (int j = lane; j < I; j += 32) x[j] = make_float2(__ldg(obs + e0 * I + j), __ldg(obs + e1 * I + j));
+            }
+            if (lane == 0) x[I] = make_float2(1.0f, 1.0f);
+        }
+        __syncwarp();
+        float2 *xin = actA, *xout = actB;
+        int sin_stride = fs.strideA, sout_stride = fs.strideB;
+        int sidx = 0;
+        for (int l = 0; l < lay.L; ++l) {
+            const int in1 = lay.in[l] + 1, out = lay.out[l];
+            for (int c = 0; c * 8 < out; ++c) {
+                // the chunk's theta rows of this lane, reused for the warp's nu pairs
+                float t[kStRows][8];
+                const float *thc = theta + lay.off[l] + (int64_t)c * in1 * 8;
+#pragma unroll
+                for (int r = 0; r < kStRows; ++r) {
+                    const int j = lane + 32 * r;
+                    float4 t03 = make_float4(0.f, 0.f, 0.f, 0.f), t47 = t03;
+                    if (j < in1) {
+                        t03 = __ldg(reinterpret_cast<const float4 *>(thc + (size_t)j * 8));
+                        t47 = __ldg(reinterpret_cast<const float4 *>(thc + (size_t)j * 8 + 4));
+                    }
+                    t[r][0] = t03.x; t[r][1] = t03.y; t[r][2] = t03.z; t[r][3] = t03.w;
+                    t[r][4] = t47.x; t[r][5] = t47.y; t[r][6] = t47.z; t[r][7] = t47.w;
+                }
+                for (int u = 0; u < nu; ++u, ++sidx) {
+                    issue(sidx + kStStages - 1);
+                    const int64_t unit = first + u;
+                    const bool is_eval = unit >= num_pairs;
+                    const float sg = is_eval ? 0.0f : sigma;
+                    const unsigned char *stage = ring + (size_t)(gc % kStStages) * fs.stage_bytes;
+                    mbar_wait(bar0 + 8u * (gc % kStStages), (gc / kStStages) & 1u);
+                    ++gc;
+                    const float2 *x = xin + (size_t)u * sin_stride;
+                    float a0[8], a1[8], b0[8], b1[8];
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) { a0[o] = 0.0f; a1[o] = 0.0f; b0[o] = 0.0f; b1[o] = 0.0f; }
+#pragma unroll
+                    for (int r = 0; r < kStRows; ++r) {
+                        const int j = lane + 32 * r;
+                        if (j < in1) {
+                            float e[8];
+                            uint4 ev = make_uint4(0u, 0u, 0u, 0u);
+                            if (!is_eval) ev = *reinterpret_cast<const uint4 *>(stage + (size_t)j * 16);
+                            halves8_to_floats(ev, e);
+                            const float2 xv = x[j];
+#pragma unroll
+                            for (int o = 0; o < 8; ++o) {
+                                a0[o] = fmaf(t[r][o], xv.x, a0[o]);
+                                a1[o] = fmaf(t[r][o], xv.y, a1[o]);
+                                b0[o] = fmaf(e[o], xv.x, b0[o]);
+                                b1[o] = fmaf(e[o], xv.y, b1[o]);
+                            }
+                        }
+                    }
+                    float v[16];
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) {
+                        v[o] = fmaf(sg, b0[o], a0[o]);       // (theta + sigma eps) . x+
+                        v[8 + o] = fmaf(-sg, b1[o], a1[o]);  // (theta - sigma eps) . x-
+                    }
+                    butterfly_step<8>(v, lane);
+                    butterfly_step<4>(v, lane);
+                    butterfly_step<2>(v, lane);
+                    butterfly_step<1>(v, lane);
+                    v[0] += __shfl_xor_sync(kAll, v[0], 1);
+                    const int o = c * 8 + om;
+                    if ((lane & 1) == 0 && o < out) {
+                        float *dst = reinterpret_cast<float *>(xout + (size_t)u * sout_stride + o) + (m >> 3);
+                        *dst = tanhf(v[0]);
+                    }
+                    __syncwarp(); // every lane is done with this eps stage
+                }
+            }
+            if (lane < nu) xout[(size_t)lane * sout_stride + out] = make_float2(1.0f, 1.0f);
+            __syncwarp();
+            float2 *tp = xin; xin = xout; xout = tp;
+            const int ts = sin_stride; sin_stride = sout_stride; sout_stride = ts;
+        }
+        // ---- actions (+ exploration noise; same semantics and streams as the generic kernel)
+        for (int u = 0; u < nu; ++u) {
+            const int64_t unit = first + u;
+            const bool is_eval = unit >= num_pairs;
+            for (int f = lane; f < 2 * OL; f += 32) {
+                const int sgn = f >= OL, o = f - sgn * OL;
+                if (sgn && is_eval) continue;
+                const int64_t e = env_of(unit, sgn);
+                const float2 xv = xin[(size_t)u * sin_stride + o];
+                float a = sgn ? xv.y : xv.x;
+                if (noise_std > 0.0f && !is_eval && num_eval > 0) {
+                    uint32_t r[4];
+                    philox4x32_10(seed ^ kEsKey, (uint64_t)(env_id_base + e), step | ((uint64_t)(o >> 2) << 48), 0u, r);
+                    float z[4];
+                    box_muller(r[0], r[1], z[0], z[1]);
+                    box_muller(r[2], r[3], z[2], z[3]);
+                    a = fmaf(noise_std, (o & 2) ? ((o & 1) ? z[3] : z[2]) : ((o & 1) ? z[1] : z[0]), a);
+                }
+                actions[e * OL + o] = a;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // gradient (parallel_mlp.py:176-218): grad[q] = sum over pairs of w[pair] * eps[pair, q], w = f+ - f-.
 // Deterministic two-stage sum: slabs of pairs -> partial[slab, q]; then the slabs in order.
 // ------------------------------------------------------------------------------------------
@@ -699,6 +898,41 @@ int fe_es_forward(const FeEsNet *net, const float *theta_packed_dev, const void 
                 lay, f, theta_packed_dev, (const __half *)eps_dev, sigma, train / 2, num_eval_envs, obs_dev,
                 (const float *)logret_dev, obs_row0_dev, obs_posfeat_dev, action_noise_std, seed, step_counter, env_id_base,
                 actions_dev);
+            return (int)cudaGetLastError();
+        }
+    }
+    // ---- streaming path: every layer has <= 319 inputs, eps chunks 16-byte granular (always), ring + activations fit
+    static const bool no_stream = getenv("FE_ES_NO_STREAM") != nullptr;
+    bool stream_ok = !no_stream;
+    for (int l = 0; l < lay.L; ++l) stream_ok = stream_ok && lay.in[l] + 1 <= 32 * kStRows;
+    if (stream_ok) {
+        StreamShape f;
+        int max_in1 = 0, a = 0, b = 0;
+        f.chunks[0] = 0;
+        for (int l = 0; l < lay.L; ++l) {
+            if (lay.in[l] + 1 > max_in1) max_in1 = lay.in[l] + 1;
+            f.chunks[l + 1] = f.chunks[l] + (lay.out[l] + 7) / 8;
+            // buffer A holds the inputs of even layers (and the outputs of odd ones), buffer B the others
+            const int need_in = lay.in[l] + 1, need_out = lay.out[l] + 1;
+            if (l % 2 == 0) { a = need_in > a ? need_in : a; b = need_out > b ? need_out : b; }
+            else { b = need_in > b ? need_in : b; a = need_out > a ? need_out : a; }
+        }
+        f.stage_bytes = (max_in1 * 16 + 127) & ~127;
+        f.strideA = (a + 1) & ~1;
+        f.strideB = (b + 1) & ~1;
+        f.U = kStMaxU;
+        while (f.U > 1 && stream_smem_bytes(f) > 226 * 1024) --f.U;
+        if (stream_smem_bytes(f) <= 226 * 1024) {
+            const size_t smem = stream_smem_bytes(f);
+            auto kern = lazy ? fe_es_forward_stream_kernel<true> : fe_es_forward_stream_kernel<false>;
+            if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
+            const int64_t units = train / 2 + num_eval_envs;
+            int64_t blocks = (units + (int64_t)kStWarps * f.U - 1) / ((int64_t)kStWarps * f.U);
+            if (blocks > num_sms[dev]) blocks = num_sms[dev];
+            kern<<<(unsigned)blocks, kStThreads, smem, (cudaStream_t)stream>>>(
+                lay, f, theta_packed_dev, (const __half *)eps_dev, sigma, train / 2, num_eval_envs, obs_dev,
+                (const float *)logret_dev, obs_row0_dev, obs_posfeat_dev, window, action_noise_std, seed, step_counter,
+                env_id_base, actions_dev);
             return (int)cudaGetLastError();
         }
     }
