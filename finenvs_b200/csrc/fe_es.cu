@@ -549,11 +549,20 @@ fe_es_forward_fast_kernel(const EsLayout lay, const FastShape fs, const float *_
 //     warp's ring, issued kStStages-1 (pair, chunk) steps ahead, completing on the stage's mbarrier;
 //   * activations of the U pairs live in shared memory as (x+, x-) float2 per input.
 // ------------------------------------------------------------------------------------------
-constexpr int kStWarps = 8;
+#ifndef FE_ES_ST_WARPS
+#define FE_ES_ST_WARPS 12
+#endif
+#ifndef FE_ES_ST_STAGES
+#define FE_ES_ST_STAGES 2
+#endif
+#ifndef FE_ES_ST_MAXU
+#define FE_ES_ST_MAXU 4
+#endif
+constexpr int kStWarps = FE_ES_ST_WARPS;
 constexpr int kStThreads = kStWarps * 32;
-constexpr int kStStages = 3;
+constexpr int kStStages = FE_ES_ST_STAGES;
 constexpr int kStRows = 10;   // rows per lane: in + 1 <= 320
-constexpr int kStMaxU = 4;
+constexpr int kStMaxU = FE_ES_ST_MAXU;
 
 struct StreamShape {
     int U;            // pairs per warp per group
@@ -587,7 +596,6 @@ fe_es_forward_stream_kernel(const EsLayout lay, const StreamShape fs, const floa
     __syncthreads();
 
     const int64_t units = num_pairs + num_eval;
-    const int total_chunks = fs.chunks[lay.L];
     const int m = lane >> 1, om = m & 7;
     auto env_of = [&](int64_t u, int sgn) -> int64_t { // :121-136 positives first, negatives second, eval envs last
         if (u >= num_pairs) return 2 * num_pairs + (u - num_pairs);
@@ -596,28 +604,30 @@ fe_es_forward_stream_kernel(const EsLayout lay, const StreamShape fs, const floa
     uint32_t gi = 0, gc = 0; // steps issued / consumed by this warp since the kernel started (stage = g % S)
     for (int64_t first = ((int64_t)blockIdx.x * kStWarps + warp) * U; first < units; first += (int64_t)gridDim.x * kStWarps * U) {
         const int nu = (int)(units - first < U ? units - first : U);
-        const int nsteps = nu * total_chunks;
-        // step s of this group = chunk s / nu (layer l, chunk c) of pair first + s % nu
-        auto issue = [&](int sidx) {
-            if (sidx >= nsteps) return;
-            const int cc = sidx / nu, u = sidx - cc * nu;
-            int l = 0;
-            while (l + 1 < lay.L && cc >= fs.chunks[l + 1]) ++l;
-            const int c = cc - fs.chunks[l], in1 = lay.in[l] + 1;
-            const int64_t unit = first + u;
+        // the steps of a group in consumption order: for every layer, for every chunk, for every pair of the warp;
+        // (il, ic, iu) walks that order one step ahead of the consumer by kStStages - 1 steps
+        int il = 0, ic = 0, iu = 0;
+        auto issue = [&]() {
+            if (il >= lay.L) return;
+            const int in1 = lay.in[il] + 1;
+            const int64_t unit = first + iu;
             const uint32_t bar = bar0 + 8u * (gi % kStStages);
             unsigned char *stage = ring + (size_t)(gi % kStStages) * fs.stage_bytes;
             ++gi;
             if (lane == 0) {
                 if (unit < num_pairs) {
                     mbar_arrive_expect_tx(bar, (uint32_t)in1 * 16u);
-                    bulk_load(smem_u32(stage), eps + unit * P + lay.off[l] + (int64_t)c * in1 * 8, (uint32_t)in1 * 16u, bar);
+                    bulk_load(smem_u32(stage), eps + unit * P + lay.off[il] + (int64_t)ic * in1 * 8, (uint32_t)in1 * 16u, bar);
                 } else {
                     mbar_arrive(bar); // evaluation env: no perturbation to fetch
                 }
             }
+            if (++iu == nu) {
+                iu = 0;
+                if (++ic * 8 >= lay.out[il]) { ic = 0; ++il; }
+            }
         };
-        for (int sidx = 0; sidx < kStStages - 1; ++sidx) issue(sidx);
+        for (int k = 0; k < kStStages - 1; ++k) issue();
         // ---- inputs of layer 0: actA[u][j] = (x of the + env, x of the - env), entry I = the constant 1 of the bias row
         for (int u = 0; u < nu; ++u) {
             const int64_t unit = first + u, e0 = env_of(unit, 0), e1 = env_of(unit, 1);
@@ -640,7 +650,6 @@ fe_es_forward_stream_kernel(const EsLayout lay, const StreamShape fs, const floa
         __syncwarp();
         float2 *xin = actA, *xout = actB;
         int sin_stride = fs.strideA, sout_stride = fs.strideB;
-        int sidx = 0;
         for (int l = 0; l < lay.L; ++l) {
             const int in1 = lay.in[l] + 1, out = lay.out[l];
             for (int c = 0; c * 8 < out; ++c) {
@@ -658,8 +667,8 @@ fe_es_forward_stream_kernel(const EsLayout lay, const StreamShape fs, const floa
                     t[r][0] = t03.x; t[r][1] = t03.y; t[r][2] = t03.z; t[r][3] = t03.w;
                     t[r][4] = t47.x; t[r][5] = t47.y; t[r][6] = t47.z; t[r][7] = t47.w;
                 }
-                for (int u = 0; u < nu; ++u, ++sidx) {
-                    issue(sidx + kStStages - 1);
+                for (int u = 0; u < nu; ++u) {
+                    issue();
                     const int64_t unit = first + u;
                     const bool is_eval = unit >= num_pairs;
                     const float sg = is_eval ? 0.0f : sigma;
