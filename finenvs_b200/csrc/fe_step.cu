@@ -843,11 +843,14 @@ fe_materialize_kernel(const int64_t N, const int W, const OutT *__restrict__ log
 // ------------------------------------------------------------------------------------------
 // portfolio variant (A > 1 assets, one cash account): EXTENSION, the reference is single-asset (:223).
 // Semantics: the reference's phases in the reference's order; inside a phase the
-// assets are visited in index order, each applying the A = 1 arithmetic to (cash, asset a).  One block
-// per env; warp 0 does the bookkeeping with lane = asset: every per-asset quantity is lane-local, only
-// the f32 cash chain is serial, walked with warp shuffles (all lanes keep an identical copy of cash).
-// Per-env sums (reward, share count) are xor-butterfly warp reductions.  The whole block then streams
-// the (W, A, 4) window in chunks: bulk copy in -> interleave 4->5 -> bulk store, double buffered.
+// cash moves ONCE: by the f64 butterfly sum of the per-asset deltas where these do not depend on cash (sales,
+// covers, margin re-mark / calls / release; bankruptcy is tested on the result), and by a greedy walk over
+// the assets in index order with an f64 running cash where they do (long and short entries: an entry is
+// legal if the cash left by the assets before it pays for it); A = 1 is the reference exactly.  One WARP per
+// env does the bookkeeping with lane = asset (fe_portfolio_book_kernel): every per-asset quantity is
+// lane-local, only the f32 cash chain is serial (all lanes keep an identical copy of cash); per-env sums
+// (reward, share count) are xor-butterfly warp reductions.  fe_portfolio_stream_kernel then streams the
+// (W, A, 4) window in chunks, one block per env: bulk copy in -> interleave 4->5 -> bulk store, double buffered.
 // ------------------------------------------------------------------------------------------
 constexpr int kPortThreads = 128;
 constexpr unsigned kFull = 0xFFFFFFFFu;
@@ -894,40 +897,36 @@ __device__ __forceinline__ void portfolio_step(const FeParams &p, const FeSeries
     float comm = 0.0f;
     float pos = d < 0.0f ? 0.0f : d, neg = d > 0.0f ? 0.0f : d;             // :344-351
     const double Omc = dsub(O, k.c), Opc = dadd(O, k.c);
-    { // :353-361 sell longs ; :367-383 cover shorts, re-mark margin (all three deltas are cash-independent)
+    { // :353-361 sell longs ; :367-374 cover shorts ; :375-383 re-mark margin.  The three cash deltas of an asset do not
+      // depend on cash: each phase adds the butterfly sum of its per-asset deltas to cash and rounds once
         const float nl = relu32(fadd(lng, neg));
         const float sold = fsub(lng, nl);
         neg = fadd(neg, sold);
         comm = fadd(comm, fmul(sold, k.cf));
         lng = nl;
-        xa[lane] = dmul((double)sold, Omc);
+        cash = d2f(dadd((double)cash, warp_sum64(act ? dmul((double)sold, Omc) : 0.0)));
         const float ns = relu32(fsub(sht, pos));
         const float bought = fsub(sht, ns);
         pos = fsub(pos, bought);
         comm = fadd(comm, fmul(bought, k.cf));
         sht = ns;
-        xb[lane] = dmul((double)bought, Opc);
+        cash = d2f(dsub((double)cash, warp_sum64(act ? dmul((double)bought, Opc) : 0.0)));
         const double nm = dmul((double)fmul(k.imrf, sht), O);
-        xc[lane] = dsub(nm, margin);
+        cash = d2f(dsub((double)cash, warp_sum64(act ? dsub(nm, margin) : 0.0)));
         margin = nm;
-        __syncwarp();
-        for (int a = 0; a < A; ++a) cash = d2f(dadd((double)cash, xa[a]));
-        for (int a = 0; a < A; ++a) {
-            cash = d2f(dsub((double)cash, xb[a]));
-            cash = d2f(dsub((double)cash, xc[a]));
-        }
-        __syncwarp();
     }
     { // :385-399 long entries, greedy in asset order
         xa[lane] = dmul((double)pos, Opc);
         __syncwarp();
         unsigned blocked_mask = 0;
+        double c = (double)cash;
         for (int a = 0; a < A; ++a) {
             const double ca = xa[a];
-            const bool blocked = dsub((double)cash, ca) < 0.0;
-            if (!blocked) cash = d2f(dsub((double)cash, ca));
+            const bool blocked = dsub(c, ca) < 0.0;
+            if (!blocked) c = dsub(c, ca);
             blocked_mask |= (blocked ? 1u : 0u) << a;
         }
+        cash = d2f(c);
         if ((blocked_mask >> lane) & 1u) pos = 0.0f;
         comm = fadd(comm, fmul(pos, k.cf));
         lng = fadd(lng, pos);
@@ -941,12 +940,14 @@ __device__ __forceinline__ void portfolio_step(const FeParams &p, const FeSeries
         xb[lane] = (double)sc;
         __syncwarp();
         unsigned blocked_mask = 0;
+        double c = (double)cash;
         for (int a = 0; a < A; ++a) {
             const double ra = xa[a], sa = xb[a];
-            const bool blocked = dsub(dsub((double)cash, ra), sa) < 0.0;
-            if (!blocked) cash = d2f(dsub((double)cash, dadd(ra, sa)));
+            const bool blocked = dsub(dsub(c, ra), sa) < 0.0;
+            if (!blocked) c = dsub(c, dadd(ra, sa));
             blocked_mask |= (blocked ? 1u : 0u) << a;
         }
+        cash = d2f(c);
         if ((blocked_mask >> lane) & 1u) { q = -0.0f; sc = fmul(q, k.cf); req = dmul(k.imr, dmul((double)q, O)); }
         comm = fadd(comm, fmul(q, k.cf));
         margin = dadd(margin, req);
@@ -962,17 +963,11 @@ __device__ __forceinline__ void portfolio_step(const FeParams &p, const FeSeries
     margin = dsub(margin, rel);
     const double mc2 = relu64(dsub(dmul(dmul((double)sht, C), k.mmr1), margin)); // :451 at Close
     margin = dadd(margin, mc2);
-    xa[lane] = mc1; xb[lane] = rel; xc[lane] = mc2;
-    __syncwarp();
-    for (int a = 0; a < A; ++a) {
-        cash = d2f(dsub((double)cash, xa[a]));
-        done |= cash < 0.0f;
-    }
-    for (int a = 0; a < A; ++a) cash = d2f(dadd((double)cash, xb[a]));
-    for (int a = 0; a < A; ++a) {
-        cash = d2f(dsub((double)cash, xc[a]));
-        done |= cash < 0.0f;
-    }
+    cash = d2f(dsub((double)cash, warp_sum64(act ? mc1 : 0.0)));                 // all margin calls at High, then :465
+    done |= cash < 0.0f;
+    cash = d2f(dadd((double)cash, warp_sum64(act ? rel : 0.0)));
+    cash = d2f(dsub((double)cash, warp_sum64(act ? mc2 : 0.0)));
+    done |= cash < 0.0f;
     double r = dadd(-mc1, -mc2);
     if (done) { lng = 0.0f; sht = 0.0f; }                                    // :452-453
     r = dadd(r, dmul((double)fsub(lng, sht), dsub(C, O)));                   // :454-455
@@ -1015,44 +1010,96 @@ __device__ __forceinline__ void portfolio_step(const FeParams &p, const FeSeries
     }
 }
 
-// smem: [2 mbarriers 16 B][pf 32 x OutT -> 256 B][scratch 3 x 32 doubles][in[2]: CH*4 OutT each][out[2]: CH*5 OutT each]
+// stream kernel smem: [2 mbarriers 16 B][pf 32 x OutT -> 256 B][unused 768 B][in[2]: CH*4 OutT each][out[2]: CH*5 OutT each]
 constexpr int kPortHeader = 16 + 256 + 768;
 template <typename OutT> __host__ __device__ inline size_t port_smem_bytes(int CH) {
     return kPortHeader + (size_t)2 * CH * 9 * sizeof(OutT);
 }
 
+// ------------------------------------------------------------------------------------------
+// portfolio kernels (A > 1): bookkeeping and streaming as two launches.  A first, fused form (one block per env: warp 0
+// bookkeeping, then the whole block streaming; profiles/r01_v4_portfolio_fused_ncu.txt) ran at 0.82 of the HBM
+// roofline: warp 0's serial cash chain (8 passes over the A assets, each a cvt -> DADD -> cvt dependency) holds its
+// block's streaming back for several microseconds per env (11.9 of 21.6 stall cycles per issue were barrier waits).  Here fe_portfolio_book_kernel runs the bookkeeping with one WARP per env at full occupancy
+// (~0.05 ms for 65 536 envs) and leaves each env's {row0, position features} as a header INSIDE the env's slice of the
+// observation tensor (the position features already at their final place in window row 0); fe_portfolio_stream_kernel
+// then reads the header and streams the window exactly as before, with nothing serial in front of it.
+// ------------------------------------------------------------------------------------------
+constexpr int kBookWarps = 4;
+
 template <typename OutT, bool kObserve>
-__global__ void __launch_bounds__(kPortThreads)
-fe_portfolio_kernel(const FeParams p, const FeSeries s, const FeState st, const Consts k,
-                    const float *__restrict__ actions, OutT *__restrict__ obs, OutT *__restrict__ rewards,
-                    int32_t *__restrict__ dones, FeStats *stats, const uint64_t step_arg,
-                    const uint64_t *__restrict__ step_dev, const int CH) {
-    extern __shared__ __align__(128) unsigned char smem[];
+__global__ void __launch_bounds__(kBookWarps * 32)
+fe_portfolio_book_kernel(const FeParams p, const FeSeries s, const FeState st, const Consts k,
+                         const float *__restrict__ actions, OutT *__restrict__ obs, OutT *__restrict__ rewards,
+                         int32_t *__restrict__ dones, FeStats *stats, const uint64_t step_arg,
+                         const uint64_t *__restrict__ step_dev) {
+    __shared__ double scratch[kBookWarps][96];
+    __shared__ OutT pf_s[kBookWarps][32];
     const uint64_t step = step_dev ? *step_dev : step_arg;
+    const int W = p.window, A = p.num_assets;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * kBookWarps + warp;
+    if (i >= p.num_envs) return; // whole warps leave together; no block-wide barrier below
+    const int32_t seg = st.seg[i];
+    const int32_t ptr = st.ptr[i] + (kObserve ? 0 : 1);
+    const int64_t row0 = __ldg(s.seg_start + seg) + ptr;
+    OutT *pf = pf_s[warp];
+    if (kObserve) {
+        if (lane < A) {
+            const double C = __ldg(s.prices + ((row0 + W - 1) * A + lane) * 4 + 3);
+            const float net = fsub(st.long_sh[i * A + lane], st.short_sh[i * A + lane]);
+            pf[lane] = (OutT)__ddiv_rn(dmul((double)net, C), k.SB);
+        }
+    } else {
+        portfolio_step<OutT>(p, s, st, k, i, seg, ptr, row0, actions, rewards, dones, stats, step, pf, scratch[warp]);
+    }
+    __syncwarp();
+    // header: row0 in the first 8 bytes of the env's slice (two words for f32 obs: the slice is only 4-byte aligned
+    // when W*A is odd), position feature of asset a at its final place, element (row 0, asset a, column 4)
+    OutT *slice = obs + (size_t)i * W * A * 5;
+    if (lane == 0) {
+        if constexpr (sizeof(OutT) == 8) {
+            reinterpret_cast<int64_t *>(slice)[0] = row0;
+        } else {
+            reinterpret_cast<uint32_t *>(slice)[0] = (uint32_t)((uint64_t)row0 & 0xFFFFFFFFu);
+            reinterpret_cast<uint32_t *>(slice)[1] = (uint32_t)((uint64_t)row0 >> 32);
+        }
+    }
+    if (lane < A) slice[(size_t)lane * 5 + 4] = pf[lane];
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(kPortThreads)
+fe_portfolio_stream_kernel(const FeParams p, const FeSeries s, OutT *__restrict__ obs, const int CH) {
+    extern __shared__ __align__(128) unsigned char smem[];
     const int W = p.window, A = p.num_assets;
     const int tid = threadIdx.x;
     const int64_t i = blockIdx.x;
     const int P = W * A;                         // (row, asset) pairs of one env's window
     const int nchunks = (P + CH - 1) / CH;
     OutT *pf = reinterpret_cast<OutT *>(smem + 16);
-    double *scratch = reinterpret_cast<double *>(smem + 16 + 256);
     unsigned char *in0 = smem + kPortHeader;
     const size_t in_bytes = (size_t)CH * 4 * sizeof(OutT), out_bytes = (size_t)CH * 5 * sizeof(OutT);
     unsigned char *out0 = in0 + 2 * in_bytes;
     const uint32_t bar0 = smem_u32(smem);
-    // every thread reads the pointer BEFORE warp 0 may overwrite it at the end of its bookkeeping
-    const int32_t seg = st.seg[i];
-    const int32_t ptr = st.ptr[i] + (kObserve ? 0 : 1);
-    const int64_t row0 = __ldg(s.seg_start + seg) + ptr;
-    const unsigned char *src = reinterpret_cast<const unsigned char *>(s.logret) + (size_t)row0 * A * 4 * sizeof(OutT);
     OutT *dst = obs + (size_t)i * P * 5;
+    // the header left by fe_portfolio_book_kernel; every thread reads row0 before anything overwrites it
+    int64_t row0;
+    if constexpr (sizeof(OutT) == 8) {
+        row0 = reinterpret_cast<const int64_t *>(dst)[0];
+    } else {
+        const uint32_t lo = reinterpret_cast<const uint32_t *>(dst)[0], hi = reinterpret_cast<const uint32_t *>(dst)[1];
+        row0 = (int64_t)(((uint64_t)hi << 32) | lo);
+    }
+    if (tid < A) pf[tid] = dst[(size_t)tid * 5 + 4];
+    const unsigned char *src = reinterpret_cast<const unsigned char *>(s.logret) + (size_t)row0 * A * 4 * sizeof(OutT);
     const bool bulk_out = (P & 3) == 0;          // then every chunk of every env is 16-byte aligned and sized
     if (tid == 0) {
         mbar_init(bar0, 1);
         mbar_init(bar0 + 8, 1);
         mbar_fence_init();
     }
-    __syncthreads();
+    __syncthreads(); // header consumed, pf visible, barriers initialised
     auto load_chunk = [&](int c) { // thread 0 only
         const int n = min(CH, P - c * CH);
         const uint32_t bytes = (uint32_t)n * 4 * sizeof(OutT);
@@ -1064,18 +1111,6 @@ fe_portfolio_kernel(const FeParams p, const FeSeries s, const FeState st, const 
         load_chunk(0);
         if (nchunks > 1) load_chunk(1);
     }
-    if (tid < 32) {
-        if (kObserve) {
-            if (tid < A) {
-                const double C = __ldg(s.prices + ((row0 + W - 1) * A + tid) * 4 + 3);
-                const float net = fsub(st.long_sh[i * A + tid], st.short_sh[i * A + tid]);
-                pf[tid] = (OutT)__ddiv_rn(dmul((double)net, C), k.SB);
-            }
-        } else {
-            portfolio_step<OutT>(p, s, st, k, i, seg, ptr, row0, actions, rewards, dones, stats, step, pf, scratch);
-        }
-    }
-    __syncthreads(); // pf visible
     const float invA = 1.0f / (float)A;
     for (int c = 0; c < nchunks; ++c) {
         const int sidx = c & 1;
@@ -1332,21 +1367,22 @@ int launch(const FeParams &p, const FeSeries &s, const FeState &st, const float 
     case K_PORTFOLIO: {
         if ((uintptr_t)obs & 15) return FE_EALIGN;
         const int P = p.window * p.num_assets;
-        int CH = 256; // pairs per chunk (4 KB in + 5 KB out, x2 stages): measured best of 128..1024 on C3 (1.73 ms)
+        int CH = 512; // pairs per chunk (8 KB in + 10 KB out, x2 stages); C3: 128 -> 1.492 ms, 256 -> 1.480, 512 -> 1.472, 1024 -> 1.471
         static const int ov_ch = env_override("FE_PORT_CHUNK");
         if (ov_ch >= 4) CH = ov_ch & ~3;
         if (CH > ((P + 3) & ~3)) CH = (P + 3) & ~3;
         const size_t smem = port_smem_bytes<OutT>(CH);
         if (smem > (size_t)kSmemMax) return FE_ESMEM;
-        auto kern = fe_portfolio_kernel<OutT, kObserve>;
-        static bool configured[16] = {false};
-        if (!configured[dev]) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+        auto skern = fe_portfolio_stream_kernel<OutT>;
+        static bool sconfigured[16] = {false};
+        if (!sconfigured[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(skern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
             if (e != cudaSuccess) return (int)e;
-            configured[dev] = true;
+            sconfigured[dev] = true;
         }
-        kern<<<(unsigned)p.num_envs, kPortThreads, smem, stream>>>(p, s, st, k, actions, (OutT *)obs, (OutT *)rewards,
-                                                                  dones, stats, step, step_dev, CH);
+        fe_portfolio_book_kernel<OutT, kObserve><<<(unsigned)((p.num_envs + kBookWarps - 1) / kBookWarps), kBookWarps * 32, 0, stream>>>(
+            p, s, st, k, actions, (OutT *)obs, (OutT *)rewards, dones, stats, step, step_dev);
+        skern<<<(unsigned)p.num_envs, kPortThreads, smem, stream>>>(p, s, (OutT *)obs, CH);
         break;
     }
     case K_SCATTER: {
@@ -1473,7 +1509,8 @@ const char *fe_step_kernel_name(const FeParams *p) {
     const bool f64 = p->out_f64 != 0;
     const StepChoice c = choose_kernel(*p, f64);
     switch (c.kern) {
-    case K_PORTFOLIO: return f64 ? "fe_portfolio_kernel<double>" : "fe_portfolio_kernel<float>";
+    case K_PORTFOLIO:
+        return f64 ? "fe_portfolio_book_kernel + fe_portfolio_stream_kernel<double>" : "fe_portfolio_book_kernel + fe_portfolio_stream_kernel<float>";
     case K_SCATTER: return f64 ? "fe_scatter_kernel<double>" : "fe_scatter_kernel<float>";
     case K_PIPE:
         return c.sin == 0 ? (f64 ? "fe_pipe_kernel<double,cached>" : "fe_pipe_kernel<float,cached>")

@@ -42,7 +42,7 @@ extern "C" {
 #define FE_VARIANT_DIRECT 2 /* warp-per-env global->global copy (any window) */
 #define FE_VARIANT_PIPE 4  /* persistent warp-specialised pipeline (bookkeeper / mover warps, multi-stage rings) */
 #define FE_VARIANT_SCATTER 5 /* persistent pipeline whose window elements land in the output tile by element-sized cp.async (no register staging) */
-#define FE_VARIANT_PORTFOLIO 3 /* block-per-env, lane-per-asset kernel; always used when num_assets > 1 */
+#define FE_VARIANT_PORTFOLIO 3 /* warp-per-env bookkeeping kernel + block-per-env streaming kernel; always used when num_assets > 1 */
 
 typedef struct FeParams {
     int64_t num_envs;        /* envs held by this GPU (a shard) */

@@ -278,11 +278,13 @@ int64_t feo_step(const FeoParams *p, const FeoSeries *s, const FeoState *st, con
 
 /* ------------------------------------------------------------------ multi-asset (A > 1) -----
  * EXTENSION with no reference implementation (the reference is single-asset, :223); SURVEY App. D.
- * Definition: shared f32 cash, per-asset long/short/margin; the reference's phases run in the
- * reference's order and INSIDE each phase the assets are visited in index order, each applying the
- * reference's A = 1 arithmetic to (cash, asset a) — so legality is evaluated against the cash left by
- * the assets before it (greedy prefix order), and A = 1 reduces to feo_step() exactly (tested on every
- * golden trace).  Per-env sums over assets (reward, share count) use the xor-butterfly order of a warp
+ * Definition: shared f32 cash, per-asset long/short/margin; the reference's phases (one per cash update
+ * of the reference: sell longs, cover shorts, re-mark margin, long entries, short entries, margin call at
+ * High, release at Low, margin call at Close) run in the reference's order, and in each phase cash moves
+ * ONCE (f64 arithmetic, one rounding to f32): where the per-asset deltas do not depend on cash, by their
+ * butterfly sum (bankruptcy is tested on the result); in the two entry phases, by a greedy walk over the
+ * assets in index order with a running f64 cash — an entry is legal if the cash left by the assets before
+ * it pays for it.  A = 1 reduces to feo_step() exactly (tested on every golden trace).  Per-env sums over assets (reward, share count) use the xor-butterfly order of a warp
  * reduction so that the CUDA kernel can reproduce them bit for bit. */
 #define FEO_MAX_ASSETS 32
 
@@ -377,65 +379,78 @@ int64_t feo_step_multi(const FeoParams *p, const FeoSeries *s, const FeoState *s
             lng[a] = st->long_sh[i * A + a]; sht[a] = st->short_sh[i * A + a]; margin[a] = st->margin[i * A + a];
             comm[a] = 0.0f;
         }
+        double dl[FEO_MAX_ASSETS];                                       /* per-asset cash deltas of a phase */
+        double c64;
         for (int a = 0; a < A; ++a) {                                    /* :353-361 */
             const float nl = relu32(lng[a] + neg[a]);
             const float sold = lng[a] - nl;
             neg[a] = neg[a] + sold;
             comm[a] = comm[a] + sold * cf;
-            cash = (float)((double)cash + (double)sold * (O[a] - c));
+            dl[a] = (double)sold * (O[a] - c);
             lng[a] = nl;
         }
-        for (int a = 0; a < A; ++a) {                                    /* :367-383 */
+        cash = (float)((double)cash + butterfly_sum64(dl, A));
+        for (int a = 0; a < A; ++a) {                                    /* :367-374 */
             const float ns = relu32(sht[a] - pos[a]);
             const float bought = sht[a] - ns;
             pos[a] = pos[a] - bought;
             comm[a] = comm[a] + bought * cf;
-            cash = (float)((double)cash - (double)bought * (O[a] + c));
+            dl[a] = (double)bought * (O[a] + c);
             sht[a] = ns;
+        }
+        cash = (float)((double)cash - butterfly_sum64(dl, A));
+        for (int a = 0; a < A; ++a) {                                    /* :375-383 */
             const double nm = (double)(imrf * sht[a]) * O[a];
-            cash = (float)((double)cash - (nm - margin[a]));
+            dl[a] = nm - margin[a];
             margin[a] = nm;
         }
+        cash = (float)((double)cash - butterfly_sum64(dl, A));
+        c64 = (double)cash;
         for (int a = 0; a < A; ++a) {                                    /* :385-399 */
-            if (((double)cash - (double)pos[a] * (O[a] + c)) < 0.0) pos[a] = 0.0f;
+            const double cost = (double)pos[a] * (O[a] + c);
+            if ((c64 - cost) < 0.0) pos[a] = 0.0f;
+            else c64 = c64 - cost;
             comm[a] = comm[a] + pos[a] * cf;
-            cash = (float)((double)cash - (double)pos[a] * (O[a] + c));
             lng[a] = lng[a] + pos[a];
         }
+        cash = (float)c64;
+        c64 = (double)cash;
         for (int a = 0; a < A; ++a) {                                    /* :401-421 */
             float q = -neg[a];
             float sc = q * cf;
             double req = imr * ((double)q * O[a]);
-            if ((((double)cash - req) - (double)sc) < 0.0) {
+            if (((c64 - req) - (double)sc) < 0.0) {
                 q = -0.0f;
                 sc = q * cf;
                 req = imr * ((double)q * O[a]);
+            } else {
+                c64 = c64 - (req + (double)sc);
             }
             comm[a] = comm[a] + q * cf;
-            cash = (float)((double)cash - (req + (double)sc));
             margin[a] = margin[a] + req;
             sht[a] = sht[a] + q;
         }
+        cash = (float)c64;
         for (int a = 0; a < A; ++a) pf[a] = ((double)(lng[a] - sht[a]) * C[a]) / SB;   /* :428-431 */
         if (obs) write_obs_multi(p, s, obs, i, row0, pf);
         int done = cash < 0.0f;                                          /* :448 */
         for (int a = 0; a < A; ++a) {                                    /* :459-468 at High */
             mc1[a] = relu64(((double)sht[a] * H[a]) * mmr1 - margin[a]);
-            cash = (float)((double)cash - mc1[a]);
             margin[a] = margin[a] + mc1[a];
-            done |= cash < 0.0f;
         }
+        cash = (float)((double)cash - butterfly_sum64(mc1, A));
+        done |= cash < 0.0f;
         for (int a = 0; a < A; ++a) {                                    /* :470-475 at Low */
-            const double rel = relu64(margin[a] - ((double)sht[a] * L[a]) * imr);
-            margin[a] = margin[a] - rel;
-            cash = (float)((double)cash + rel);
+            dl[a] = relu64(margin[a] - ((double)sht[a] * L[a]) * imr);
+            margin[a] = margin[a] - dl[a];
         }
+        cash = (float)((double)cash + butterfly_sum64(dl, A));
         for (int a = 0; a < A; ++a) {                                    /* :451 at Close */
             mc2[a] = relu64(((double)sht[a] * C[a]) * mmr1 - margin[a]);
-            cash = (float)((double)cash - mc2[a]);
             margin[a] = margin[a] + mc2[a];
-            done |= cash < 0.0f;
         }
+        cash = (float)((double)cash - butterfly_sum64(mc2, A));
+        done |= cash < 0.0f;
         float held[FEO_MAX_ASSETS];
         for (int a = 0; a < A; ++a) {
             double ra = (-mc1[a]) + (-mc2[a]);
