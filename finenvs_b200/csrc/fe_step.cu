@@ -841,6 +841,100 @@ fe_materialize_kernel(const int64_t N, const int W, const OutT *__restrict__ log
 }
 
 // ------------------------------------------------------------------------------------------
+// split variant: bookkeeping and streaming as two launches (what made the portfolio path 25 % faster).
+//   fe_book_kernel    one THREAD per env at full occupancy runs env_step() and leaves {row0, position feature} as a
+//                     header inside the env's slice of the observation tensor (row0 in its first 8 bytes, the feature
+//                     at element 4 = its final place in window row 0);
+//   fe_stream_kernel  one WARP per env, no shared memory, no barriers: lane l produces output elements l, l+32, ... of
+//                     the env's W*5 values — element f is column f%5 of window row f/5, i.e. input element f - f/5 or
+//                     the position feature — so every store instruction writes 128 contiguous bytes and every load
+//                     instruction reads ~104 contiguous bytes of the staged series; ceil(5W/32) independent loads per
+//                     lane are in flight at once and 48 warps per SM hide the L2 / HBM latency.
+// ------------------------------------------------------------------------------------------
+template <typename OutT, bool kObserve>
+__global__ void __launch_bounds__(kThreads)
+fe_book_kernel(const FeParams p, const FeSeries s, const FeState st, const Consts k, const float *__restrict__ actions,
+               OutT *__restrict__ obs, OutT *__restrict__ rewards, int32_t *__restrict__ dones, FeStats *stats,
+               const uint64_t step_arg, const uint64_t *__restrict__ step_dev) {
+    const uint64_t step = step_dev ? *step_dev : step_arg;
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const bool active = i < p.num_envs;
+    EnvResult r;
+    r.done = 0; r.newly_terminated = 0; r.fin_return = 0.0; r.fin_len = 0; r.row0 = 0; r.posfeat = 0.0;
+    if (active) {
+        if (kObserve) r = env_observe(p, s, st, k, i);
+        else r = env_step<OutT>(p, s, st, k, i, actions, rewards, dones, stats != nullptr, step);
+        OutT *slice = obs + (size_t)i * p.window * 5;
+        if constexpr (sizeof(OutT) == 8) {
+            reinterpret_cast<int64_t *>(slice)[0] = r.row0;
+        } else { // the slice is only 4-byte aligned when W is odd: two words
+            reinterpret_cast<uint32_t *>(slice)[0] = (uint32_t)((uint64_t)r.row0 & 0xFFFFFFFFu);
+            reinterpret_cast<uint32_t *>(slice)[1] = (uint32_t)((uint64_t)r.row0 >> 32);
+        }
+        slice[4] = (OutT)r.posfeat;
+    }
+    if (!kObserve) accumulate_stats(stats, r, active);
+}
+
+constexpr int kStreamThreads = 256;
+constexpr int kStreamSlots = 15;                   // output elements per lane and batch whose loads are in flight together
+constexpr int kStreamSpan = 32 * kStreamSlots;     // 480 output elements = 96 window rows: a multiple of 5, so the
+constexpr int kStreamSpanIn = kStreamSpan / 5 * 4; // (row, column) pattern of a lane's slots is the same in every batch
+template <typename OutT>
+__global__ void __launch_bounds__(kStreamThreads)
+fe_stream_kernel(const int64_t N, const int W, const OutT *__restrict__ logret, OutT *__restrict__ obs) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * kStreamThreads + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * kStreamThreads) >> 5;
+    const int n = W * 5;
+    // slot u of this lane is output element g = lane + 32u of a batch: input element g - g/5, or the position feature
+    int off[kStreamSlots];
+#pragma unroll
+    for (int u = 0; u < kStreamSlots; ++u) {
+        const int g = lane + 32 * u;
+        off[u] = g % 5 == 4 ? -1 : g - g / 5;
+    }
+    const int nfull = n / kStreamSpan, tail = n - nfull * kStreamSpan; // elements of the last, partial batch
+    auto header = [&](int64_t e, int64_t &row0, OutT &pf) {
+        const OutT *slice = obs + (size_t)e * n;
+        if constexpr (sizeof(OutT) == 8) {
+            row0 = reinterpret_cast<const int64_t *>(slice)[0];
+        } else {
+            const uint32_t lo = reinterpret_cast<const uint32_t *>(slice)[0], hi = reinterpret_cast<const uint32_t *>(slice)[1];
+            row0 = (int64_t)(((uint64_t)hi << 32) | lo);
+        }
+        pf = slice[4];
+    };
+    int64_t row0 = 0, row0_next = 0;
+    OutT pf = 0, pf_next = 0;
+    if (warp0 < N) header(warp0, row0, pf);
+    for (int64_t e = warp0; e < N; e += nwarps) {
+        // the next env's header travels while this env's window does (a warp's envs are nwarps apart: other slices)
+        if (e + nwarps < N) header(e + nwarps, row0_next, pf_next);
+        OutT *out = obs + (size_t)e * n + lane;
+        const OutT *src = logret + row0 * 4;
+        __syncwarp(); // every lane holds this env's header before any lane overwrites it
+        for (int b = 0; b < nfull; ++b, out += kStreamSpan, src += kStreamSpanIn) {
+            OutT v[kStreamSlots];
+#pragma unroll
+            for (int u = 0; u < kStreamSlots; ++u) v[u] = off[u] >= 0 ? __ldg(src + off[u]) : pf;
+#pragma unroll
+            for (int u = 0; u < kStreamSlots; ++u) out[32 * u] = v[u];
+        }
+        if (tail > 0) {
+            OutT v[kStreamSlots];
+#pragma unroll
+            for (int u = 0; u < kStreamSlots; ++u) v[u] = (off[u] >= 0 && lane + 32 * u < tail) ? __ldg(src + off[u]) : pf;
+#pragma unroll
+            for (int u = 0; u < kStreamSlots; ++u)
+                if (lane + 32 * u < tail) out[32 * u] = v[u];
+        }
+        row0 = row0_next;
+        pf = pf_next;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // portfolio variant (A > 1 assets, one cash account): EXTENSION, the reference is single-asset (:223).
 // Semantics: the reference's phases in the reference's order; inside a phase the
 // cash moves ONCE: by the f64 butterfly sum of the per-asset deltas where these do not depend on cash (sales,
@@ -1297,12 +1391,13 @@ int pick_pipe_stages(const FeParams &p, bool f64) {
 }
 
 
-// Which kernel a launch uses.  `auto`: portfolio when A > 1; the persistent pipe variant for populations that give every
+// Which kernel a launch uses.  `auto`: portfolio when A > 1; split for windows too long for the pipe variant; the
+// persistent pipe variant for populations that give every
 // SM a few tiles AND windows of >= 24 rows (measured on c2, tools/window_sweep.sh -> profiles/r01_v4_window_sweep.txt:
 // W = 4 / 16: tile 0.19 / 0.24 ms vs pipe 0.73 / 0.37 ms — with so few rows per env the 6 bookkeeper warps are the
 // bottleneck, while the tile variant gives every env its own thread; W = 60 / 128 / 390: pipe 0.27 / 0.27 / 0.23 vs tile
 // 0.36 / 0.38 / 0.29); else tile while the window fits in shared memory; else direct.
-enum StepKernel { K_PORTFOLIO, K_SCATTER, K_PIPE, K_TILE, K_DIRECT, K_ERR_SMEM };
+enum StepKernel { K_PORTFOLIO, K_SPLIT, K_SCATTER, K_PIPE, K_TILE, K_DIRECT, K_ERR_SMEM };
 struct StepChoice {
     StepKernel kern;
     int te;      // envs per tile (pipe / scatter / tile)
@@ -1313,6 +1408,8 @@ struct StepChoice {
 StepChoice choose_kernel(const FeParams &p, bool f64) {
     StepChoice c = {K_DIRECT, 0, 0, 0, 0, kThreads};
     if (p.num_assets > 1 || p.variant == FE_VARIANT_PORTFOLIO) { c.kern = K_PORTFOLIO; return c; }
+    static const int auto_split = env_override("FE_AUTO_SPLIT");     // sweeps: 1 = "auto" prefers split, -1 = never
+    if ((p.variant == FE_VARIANT_SPLIT || (p.variant == FE_VARIANT_AUTO && auto_split > 0))) { c.kern = K_SPLIT; return c; }
     static const int auto_scatter = env_override("FE_AUTO_SCATTER"); // sweeps: 1 = "auto" prefers scatter
     static const int no_pipe = env_override("FE_NO_PIPE");           // sweeps: "auto" never picks pipe
     // small populations: a persistent grid needs a few tiles per SM to hide its prologue
@@ -1327,6 +1424,9 @@ StepChoice choose_kernel(const FeParams &p, bool f64) {
         c.te = pick_pipe_envs(p.window, f64, c.sin);
         if (c.te == 0 && p.variant == FE_VARIANT_PIPE) { c.kern = K_ERR_SMEM; return c; }
         if (c.te > 0 && (p.variant == FE_VARIANT_PIPE || (worth_persistent && p.window >= 24))) { c.kern = K_PIPE; return c; }
+        // windows too long for the pipe variant's rings (> 512 rows f32, > 256 f64): the split variant's warp-per-env
+        // streaming (W = 1024, 64 Ki envs: 0.26 ms vs 0.66 ms for tile)
+        if (c.te == 0 && p.variant == FE_VARIANT_AUTO && auto_split >= 0) { c.kern = K_SPLIT; return c; }
     }
     c.te = p.variant == FE_VARIANT_DIRECT ? 0 : pick_tile_envs(p.window, f64, &c.threads);
     if (p.variant == FE_VARIANT_TILE && c.te == 0) { c.kern = K_ERR_SMEM; return c; }
@@ -1383,6 +1483,19 @@ int launch(const FeParams &p, const FeSeries &s, const FeState &st, const float 
         fe_portfolio_book_kernel<OutT, kObserve><<<(unsigned)((p.num_envs + kBookWarps - 1) / kBookWarps), kBookWarps * 32, 0, stream>>>(
             p, s, st, k, actions, (OutT *)obs, (OutT *)rewards, dones, stats, step, step_dev);
         skern<<<(unsigned)p.num_envs, kPortThreads, smem, stream>>>(p, s, (OutT *)obs, CH);
+        break;
+    }
+    case K_SPLIT: {
+        if ((uintptr_t)obs & 7) return FE_EALIGN;
+        int rc = device_sm_count(p.device, &sms);
+        if (rc) return rc;
+        fe_book_kernel<OutT, kObserve><<<(unsigned)((p.num_envs + kThreads - 1) / kThreads), kThreads, 0, stream>>>(
+            p, s, st, k, actions, (OutT *)obs, (OutT *)rewards, dones, stats, step, step_dev);
+        static const int ov_b = env_override("FE_STREAM_BLOCKS_PER_SM");
+        int64_t blocks = (int64_t)sms * (ov_b > 0 ? ov_b : 6); // 48 warps per SM
+        const int64_t need = (p.num_envs * 32 + kStreamThreads - 1) / kStreamThreads;
+        if (blocks > need) blocks = need;
+        fe_stream_kernel<OutT><<<(unsigned)blocks, kStreamThreads, 0, stream>>>(p.num_envs, p.window, (const OutT *)s.logret, (OutT *)obs);
         break;
     }
     case K_SCATTER: {
@@ -1511,6 +1624,7 @@ const char *fe_step_kernel_name(const FeParams *p) {
     switch (c.kern) {
     case K_PORTFOLIO:
         return f64 ? "fe_portfolio_book_kernel + fe_portfolio_stream_kernel<double>" : "fe_portfolio_book_kernel + fe_portfolio_stream_kernel<float>";
+    case K_SPLIT: return f64 ? "fe_book_kernel + fe_stream_kernel<double>" : "fe_book_kernel + fe_stream_kernel<float>";
     case K_SCATTER: return f64 ? "fe_scatter_kernel<double>" : "fe_scatter_kernel<float>";
     case K_PIPE:
         return c.sin == 0 ? (f64 ? "fe_pipe_kernel<double,cached>" : "fe_pipe_kernel<float,cached>")

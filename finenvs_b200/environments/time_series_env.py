@@ -35,7 +35,7 @@ except Exception:  # pragma: no cover - gym is not installed in the target image
 
 _RESET_MODES = {"keep": _lib.RESET_KEEP, "last": _lib.RESET_LAST, "all": _lib.RESET_ALL}
 _VARIANTS = {"auto": _lib.VARIANT_AUTO, "tile": _lib.VARIANT_TILE, "direct": _lib.VARIANT_DIRECT,
-             "portfolio": _lib.VARIANT_PORTFOLIO, "pipe": _lib.VARIANT_PIPE, "scatter": _lib.VARIANT_SCATTER}
+             "portfolio": _lib.VARIANT_PORTFOLIO, "pipe": _lib.VARIANT_PIPE, "scatter": _lib.VARIANT_SCATTER, "split": _lib.VARIANT_SPLIT}
 
 
 class LazyObs:

@@ -41,6 +41,7 @@ extern "C" {
 #define FE_VARIANT_TILE 1   /* cp.async.bulk in -> smem interleave -> cp.async.bulk out */
 #define FE_VARIANT_DIRECT 2 /* warp-per-env global->global copy (any window) */
 #define FE_VARIANT_PIPE 4  /* persistent warp-specialised pipeline (bookkeeper / mover warps, multi-stage rings) */
+#define FE_VARIANT_SPLIT 6   /* two launches: thread-per-env bookkeeping, then warp-per-env streaming with fully coalesced stores */
 #define FE_VARIANT_SCATTER 5 /* persistent pipeline whose window elements land in the output tile by element-sized cp.async (no register staging) */
 #define FE_VARIANT_PORTFOLIO 3 /* warp-per-env bookkeeping kernel + block-per-env streaming kernel; always used when num_assets > 1 */
 

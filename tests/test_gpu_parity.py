@@ -31,7 +31,8 @@ def _env(series, **kw):
                                            (torch.float64, "direct"), (torch.float32, "portfolio"),
                                            (torch.float64, "portfolio"), (torch.float32, "pipe"),
                                            (torch.float64, "pipe"), (torch.float32, "scatter"),
-                                           (torch.float64, "scatter")])
+                                           (torch.float64, "scatter"), (torch.float32, "split"),
+                                           (torch.float64, "split")])
 def test_cuda_replays_reference_trace(name, dtype, variant):
     z = load_trace(name)
     if variant == "pipe" and _lib_mod().lib().fe_pipe_envs(int(z["window"]), int(dtype == torch.float64), 0) == 0:
@@ -459,7 +460,7 @@ def test_flat_obs_and_es_env_args():
     assert o0.shape == (500, W * 5) and int(b._ptr.abs().sum()) == 0 and float(b._cash.min()) == 10000.0
 
 
-@pytest.mark.parametrize("variant", ["pipe", "scatter"])
+@pytest.mark.parametrize("variant", ["pipe", "scatter", "split"])
 @pytest.mark.parametrize("W,N,dtype", [(60, 1024, torch.float32), (60, 5003, torch.float32), (60, 4099, torch.float64),
                                        (8, 70001, torch.float32), (128, 3000, torch.float32), (3, 999, torch.float32)])
 def test_pipe_variant_vs_oracle(W, N, dtype, variant):
