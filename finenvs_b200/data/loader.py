@@ -67,21 +67,31 @@ class HostSeries:
 
 
 def _seconds_of_day(times) -> np.ndarray:
-    parts = times.astype(str).str.split(":", expand=True)
+    """Seconds since midnight of "HH:MM[:SS]" strings.  A trading file has at most a few thousand DISTINCT times:
+    they are factorised (one hash pass) and only the distinct strings are parsed."""
+    import pandas as pd
+
+    codes, uniques = pd.factorize(times)
+    parts = pd.Series(uniques).astype(str).str.split(":", expand=True)
     secs = parts[0].astype(np.int64) * 3600 + parts[1].astype(np.int64) * 60
     if parts.shape[1] > 2:
         secs = secs + parts[2].fillna(0).astype(float).astype(np.int64)
-    return secs.to_numpy()
+    return secs.to_numpy()[codes]
 
 
 def segment_table(dates: np.ndarray, window: int):
     """First/last row of every distinct Date (:141-152), backtracked by W rows of history; days
-    whose history would start before row 0 are skipped (:134).  Order = first appearance."""
-    codes, first, inv = np.unique(dates, return_index=True, return_inverse=True)
-    last = np.zeros(len(codes), dtype=np.int64)
-    np.maximum.at(last, inv, np.arange(len(dates), dtype=np.int64))
-    order = np.argsort(first, kind="stable")
-    first, last = first[order].astype(np.int64), last[order]
+    whose history would start before row 0 are skipped (:134).  Order = first appearance.  One hash pass over the
+    rows (the reference scans the whole frame once per day)."""
+    import pandas as pd
+
+    inv, uniques = pd.factorize(dates)          # codes in order of first appearance
+    n = len(uniques)
+    idx = np.arange(len(dates), dtype=np.int64)
+    first = np.full(n, len(dates), dtype=np.int64)
+    last = np.zeros(n, dtype=np.int64)
+    np.minimum.at(first, inv, idx)
+    np.maximum.at(last, inv, idx)
     start = first - window
     keep = start >= 0
     return start[keep], (last[keep] - start[keep] + 1).astype(np.int32)
@@ -96,7 +106,7 @@ def read_market_csv(path: str, window: int) -> HostSeries:
     keep = (secs >= MARKET_OPEN_S) & (secs <= MARKET_CLOSE_S)
     df = df[keep]
     prices = np.ascontiguousarray(df[["Open", "High", "Low", "Close"]].to_numpy(dtype=np.float64))
-    seg_start, seg_len_raw = segment_table(df["Date"].to_numpy().astype(str), window)
+    seg_start, seg_len_raw = segment_table(df["Date"].to_numpy(), window)
     if len(seg_start) == 0:
         raise Exception(f"{path}: no trading day has {window} bars of history before it")
     return HostSeries(prices, seg_start, seg_len_raw)
