@@ -1,7 +1,7 @@
-"""Mirror of the reference's finenvs/base_object.py:7-9 (every reference class exposes .print())."""
-from pprint import pprint
+"""Every reference class exposes `.print()` (finenvs/base_object.py:7-9): a dump of the instance's attributes."""
+import pprint as _pprint
 
 
-class BaseObject(object):
+class BaseObject:
     def print(self) -> None:
-        pprint(vars(self))
+        _pprint.pprint(self.__dict__)

@@ -7,11 +7,10 @@ import torch
 
 
 def set_device(device_id: int) -> str:
-    if torch.cuda.is_available() and device_id >= 0:
-        return f"cuda:{device_id}"
-    else:
+    use_cuda = device_id >= 0 and torch.cuda.is_available()
+    if not use_cuda:  # the message is part of the reference's observable behaviour (device_utils.py:8)
         print("WARNING: PyTorch not recognizing CUDA device -> forcing CPU...")
-        return "cpu"
+    return f"cuda:{device_id}" if use_cuda else "cpu"
 
 
 def require_cuda_device(device_id: int) -> str:
