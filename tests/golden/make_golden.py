@@ -43,11 +43,18 @@ def csv_arrays(path: str) -> dict:
 
 
 def trace(csv: str, window: int, steps: int, seed: int, *, evaluate=False, widen=None, action_fn=None,
-          scripted=None, store_all_obs=False, max_obs_steps=10) -> dict:
-    r = rh.RefEnv(csv, "dummy", window, seed=seed, evaluate=evaluate)
+          scripted=None, store_all_obs=False, max_obs_steps=10, params=None) -> dict:
+    """`params`: (max_shares, starting_balance, per_share_commission, initial_margin_requirement,
+    maintenance_margin_requirement) when they differ from the reference's defaults (time_series_env.py:20-26)."""
+    ref_kw = {}
+    if params is not None:
+        ref_kw = dict(max_shares=int(params[0]), starting_balance=float(params[1]), per_share_commission=float(params[2]),
+                      initial_margin_requirement=float(params[3]), maintenance_margin_requirement=float(params[4]))
+    r = rh.RefEnv(csv, "dummy", window, seed=seed, evaluate=evaluate, **ref_kw)
     fs = rh.flat_series_from_ref(r)
     out = {
         "window": window, "seed": seed, "evaluate": int(evaluate),
+        "params": np.array(params if params is not None else (5, 10000.0, 0.01, 1.5, 0.25), dtype=np.float64),
         "prices": fs.prices, "logret": fs.logret, "seg_start": fs.seg_start, "seg_len_raw": fs.seg_len_raw,
         "pe_shape": np.array(r.env.price_environments.shape),
         "pe_digest": digest(r.env.price_environments.numpy()),
@@ -142,6 +149,23 @@ def main():
             rh.write_csv(p, dates, times, ohlc)
             t = trace(p, 8, 300, seed, widen=96, action_fn=short_biased(frac), max_obs_steps=12)
             np.savez_compressed(f"trace_adv_{tag}_w8_n96.npz", **t)
+
+    # ---- every constructor parameter off its default (time_series_env.py:20-26), ragged days, actions beyond [-1, 1]
+    with tempfile.TemporaryDirectory() as td:
+        for tag, seed, W, sigma, s0, params, ev in [
+            ("p1", 31, 5, 0.08, 40.0, (40, 500.0, 0.37, 2.25, 0.4), False),
+            ("p2", 32, 3, 0.2, 3.0, (1, 250000.0, 0.0, 1.0, 0.1), True),
+            ("p3", 33, 9, 0.02, 900.0, (12, 20000.0, 0.05, 1.2, 0.3), False),
+        ]:
+            rng = np.random.default_rng(seed)
+            bars = [W + 3, 20, 1, 14, 31, 2, 9, 20, 5]
+            dates, times = day_labels(len(bars), bars)
+            p = os.path.join(td, f"par_{tag}.csv")
+            rh.write_csv(p, dates, times, gbm_ohlc(rng, sum(bars), sigma, s0=s0))
+            bias = {"p1": -0.4, "p2": 0.3, "p3": 0.0}[tag]
+            t = trace(p, W, 220, seed, evaluate=ev, widen=64, params=params, max_obs_steps=8,
+                      action_fn=lambda r, n, b=bias: np.clip(r.normal(b, 0.8, n), -1.3, 1.3).astype(np.float32))
+            np.savez_compressed(f"trace_par_{tag}_w{W}_n64.npz", **t)
 
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

@@ -73,6 +73,13 @@ def load_trace(name: str):
         return {k: z[k] for k in z.files}   # materialise once (NpzFile re-inflates on every access)
 
 
+def trace_params(z) -> dict:
+    """(max_shares, starting_balance, commission, imr, mmr) the reference was constructed with (defaults in old traces)."""
+    v = z["params"] if "params" in z else np.array([5, 10000.0, 0.01, 1.5, 0.25])
+    return {"max_shares": int(v[0]), "starting_balance": float(v[1]), "commission": float(v[2]), "imr": float(v[3]),
+            "mmr": float(v[4])}
+
+
 def trace_series(z):
     from oracle import oracle as orc
 

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from parity_utils import (CudaAdapter, assert_bits_equal, assert_state_equal, gbm_ohlc, golden_traces, load_trace,
+from parity_utils import (CudaAdapter, assert_bits_equal, assert_state_equal, gbm_ohlc, golden_traces, load_trace, trace_params,
                           oracle_state, replay_trace, stage_trace_series)
 
 pytestmark = pytest.mark.gpu
@@ -41,7 +41,10 @@ def test_cuda_replays_reference_trace(name, dtype, variant):
         pytest.skip("window too large for the scatter variant's ring (4 stages of 4 envs)")
     series = stage_trace_series(z, dtype)
     N = len(z["seg_init"])
-    env = _env(series, num_envs=N, evaluate=bool(z["evaluate"]), seed=int(z["seed"]), obs_dtype=dtype, variant=variant)
+    tp = trace_params(z)
+    env = _env(series, num_envs=N, evaluate=bool(z["evaluate"]), seed=int(z["seed"]), obs_dtype=dtype, variant=variant,
+               max_shares=tp["max_shares"], starting_balance=tp["starting_balance"], per_share_commission=tp["commission"],
+               initial_margin_requirement=tp["imr"], maintenance_margin_requirement=tp["mmr"])
     env._seg.copy_(torch.from_numpy(z["seg_init"]))
     ad = CudaAdapter(env)
     replay_trace(z, ad, ad.state, dtype == torch.float64, f"{name}[{variant}]")
@@ -506,3 +509,45 @@ def test_step_host_pipeline_equals_device_step(N, A, dtype):
             assert torch.equal(getattr(a_env, k), getattr(b_env, k)), k
     sa, sb = a_env.stats(), b_env.stats()
     assert int(sa["n_done"]) == int(sb["n_done"]) > 0 and int(sa["sum_len"]) == int(sb["sum_len"])
+
+
+@pytest.mark.parametrize("variant,A,N", [("tile", 1, 3001), ("pipe", 1, 40000), ("split", 1, 5003), ("auto", 3, 2500)])
+@pytest.mark.parametrize("params", [(40, 500.0, 0.37, 2.25, 0.4), (1, 250000.0, 0.0, 1.0, 0.1), (12, 20000.0, 0.05, 1.2, 0.3)])
+def test_non_default_parameters_vs_oracle(variant, A, N, params):
+    """Every constructor parameter of the reference off its default (time_series_env.py:20-26; the three golden
+    trace_par_* files pin the same parameter sets to the real reference): kernels vs oracle at larger N, A = 3 included."""
+    from oracle import oracle as orc
+    from finenvs_b200.data import loader
+
+    W = 10
+    ms, sb, com, imr, mmr = params
+    if A == 1:
+        prices, seg_start, seg_len = _c1_series(W, days=60, bars=33, sigma=0.06, seed=int(ms) + N)
+    else:
+        prices, seg_start, seg_len = _portfolio_series(A, W, 60, 33, 0.06, int(ms) + N)
+    series = loader.stage_series(prices, seg_start, seg_len, W, "cuda:0", torch.float32, keep_logret64=True)
+    fs = orc.series_from_prices(prices, seg_start, seg_len, W, logret=series.logret64.cpu().numpy())
+    env = _env(series, num_envs=N, seed=6, random_reset="all", random_offset=True, variant=variant, track_stats=True,
+               max_shares=int(ms), starting_balance=sb, per_share_commission=com, initial_margin_requirement=imr,
+               maintenance_margin_requirement=mmr)
+    ref = orc.OracleEnv(fs, num_envs=N, seed=6, reset_mode=2, random_offset=True, out_f64=False, max_shares=int(ms),
+                        starting_balance=sb, commission=com, imr=imr, mmr=mmr)
+    rng = np.random.default_rng(N)
+    ad = CudaAdapter(env)
+    assert_bits_equal(ref.reset(), ad.reset(), "reset obs")
+    n_done = 0
+    for t in range(70):
+        a = np.clip(rng.normal(-0.2, 0.8, (N, A)), -1.3, 1.3).astype(np.float32)
+        o_ref, r_ref, d_ref, _ = ref.step(a if A > 1 else a.reshape(-1))
+        o, r, d, _ = ad.step(a)
+        assert_bits_equal(d_ref, d, f"dones t={t}")
+        st = ad.state()
+        for key in ("seg", "ptr", "cash"):
+            assert_bits_equal(getattr(ref, key), st[key], f"{key} t={t}")
+        for key in ("long_sh", "short_sh", "margin"):
+            assert_bits_equal(getattr(ref, key).reshape(-1), st[key], f"{key} t={t}")
+        assert_bits_equal(r_ref, r, f"rewards t={t}")
+        if t % 5 == 0:
+            assert_bits_equal(o_ref, o, f"obs t={t}")
+        n_done += int(d_ref.sum())
+    assert n_done > 0 and int(env.stats()["n_done"].item()) == n_done

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as orc
-from parity_utils import golden_traces, load_trace, oracle_state, replay_trace, trace_series
+from parity_utils import golden_traces, load_trace, oracle_state, replay_trace, trace_params, trace_series
 
 
 @pytest.mark.parametrize("name", golden_traces())
@@ -14,7 +14,7 @@ def test_oracle_replays_reference_trace(name, out_f64, multi):
     z = load_trace(name)
     fs = trace_series(z)
     env = orc.OracleEnv(fs, num_envs=len(z["seg_init"]), evaluate=bool(z["evaluate"]), seed=int(z["seed"]),
-                        seg_init=z["seg_init"], out_f64=out_f64, force_multi=multi)
+                        seg_init=z["seg_init"], out_f64=out_f64, force_multi=multi, **trace_params(z))
     replay_trace(z, env, lambda: oracle_state(env), out_f64, name)
     # the redraws the reference consumed are the oracle's own Philox draws
     for step, kind, seg in z["draw_log"]:

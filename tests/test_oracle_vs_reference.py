@@ -11,8 +11,8 @@ from parity_utils import assert_bits_equal, assert_state_equal, day_labels, gbm_
 pytestmark = pytest.mark.skipif(not rh.available(), reason="reference checkout not present")
 
 
-def _lockstep(csv, W, steps, seed, evaluate=False, widen=None, action_fn=None):
-    r = rh.RefEnv(csv, "dummy", W, seed=seed, evaluate=evaluate)
+def _lockstep(csv, W, steps, seed, evaluate=False, widen=None, action_fn=None, ref_kw=None, orc_kw=None):
+    r = rh.RefEnv(csv, "dummy", W, seed=seed, evaluate=evaluate, **(ref_kw or {}))
     try:
         fs_ref = rh.flat_series_from_ref(r)
         fs = orc.load_csv(csv, W)  # the oracle's own loader restatement
@@ -26,7 +26,7 @@ def _lockstep(csv, W, steps, seed, evaluate=False, widen=None, action_fn=None):
         if widen:
             seg_init = np.arange(widen) % fs.num_segments
             r.widen(seg_init)
-        o = orc.OracleEnv(fs_ref, num_envs=widen, evaluate=evaluate, seed=seed, seg_init=seg_init)
+        o = orc.OracleEnv(fs_ref, num_envs=widen, evaluate=evaluate, seed=seed, seg_init=seg_init, **(orc_kw or {}))
         assert_state_equal(r.state(), oracle_state(o), "init")
         assert_bits_equal(r.reset(), o.reset(), "reset obs")
         rng = np.random.default_rng(seed + 1)
@@ -71,3 +71,33 @@ def test_widened_adversarial_series(tmp_path):
         return a.astype(np.float32)
 
     assert _lockstep(p, 6, 250, seed=23, widen=64, action_fn=act) > 500
+
+
+@pytest.mark.parametrize("case", range(10))
+def test_fuzzed_series_and_parameters(tmp_path, case):
+    """Seeded fuzz: ragged days (1-bar and short days included), volatility from calm to violent, every constructor
+    parameter of the reference moved off its default (time_series_env.py:15-29), both modes — bit for bit."""
+    rng = np.random.default_rng(1000 + case)
+    W = int(rng.integers(1, 13))
+    days = int(rng.integers(5, 12))
+    bars = [int(b) for b in rng.choice([1, 2, 3, 5, 9, 14, 20, 31], size=days)]
+    bars[0] = max(bars[0], W + 1)                       # the first day only provides history (:134)
+    sigma = float(rng.choice([0.004, 0.02, 0.08, 0.2]))
+    dates, times = day_labels(days, bars)
+    p = str(tmp_path / f"fuzz{case}.csv")
+    rh.write_csv(p, dates, times, gbm_ohlc(rng, sum(bars), sigma, s0=float(rng.choice([3.0, 40.0, 900.0]))))
+    max_shares = int(rng.choice([1, 5, 40]))
+    balance = float(rng.choice([500.0, 10000.0, 250000.0]))
+    commission = float(rng.choice([0.0, 0.01, 0.37]))
+    imr = float(rng.choice([1.0, 1.5, 2.25]))
+    mmr = float(rng.choice([0.1, 0.25, 0.4]))
+    evaluate = bool(case % 3 == 0)
+    ref_kw = dict(max_shares=max_shares, starting_balance=balance, per_share_commission=commission,
+                  initial_margin_requirement=imr, maintenance_margin_requirement=mmr)
+    orc_kw = dict(max_shares=max_shares, starting_balance=balance, commission=commission, imr=imr, mmr=mmr)
+    bias = float(rng.uniform(-0.6, 0.6))
+
+    def act(r, n):                                      # exceeds [-1, 1] now and then: the env clamps (:301)
+        return np.clip(r.normal(bias, 0.8, n), -1.3, 1.3).astype(np.float32)
+
+    _lockstep(p, W, 160, seed=2000 + case, evaluate=evaluate, widen=48, action_fn=act, ref_kw=ref_kw, orc_kw=orc_kw)
