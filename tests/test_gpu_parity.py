@@ -551,3 +551,52 @@ def test_non_default_parameters_vs_oracle(variant, A, N, params):
             assert_bits_equal(o_ref, o, f"obs t={t}")
         n_done += int(d_ref.sum())
     assert n_done > 0 and int(env.stats()["n_done"].item()) == n_done
+
+
+@pytest.mark.parametrize("trace,instr,how", [("trace_ibm_w60.npz", "IBM", "env_var"), ("trace_oih_w60_eval.npz", "OIH", "path"),
+                                             ("trace_spy_w390.npz", "SPY", "path"), ("kat_ibm_w390.npz", "IBM", "env_var")])
+def test_drop_in_constructor_from_csv_replays_the_reference(tmp_path, monkeypatch, trace, instr, how):
+    """The constructor a reference user calls — TimeSeriesEnv("IBM", "dummy", num_intervals=60) on a data directory
+    with the reference's CSV (:15-45, :80-216) — end to end: CSV loader, staging, GPU log-returns, reference defaults
+    (num_envs = days (+1 when training), last-env redraws).  State, rewards and dones replay the reference's trace
+    exactly; observations to 1e-12 absolute in f64 (fe_log_returns' log vs torch's: <= 2 ulp of a value of O(1))."""
+    from finenvs_b200.environments import TimeSeriesEnv
+
+    z = load_trace(trace)
+    zc = load_trace("dummy_csv.npz")
+    W = int(z["window"])
+    base = tmp_path / "root"
+    d = base / instr if how == "env_var" else tmp_path / f"data_{instr}"      # a path containing "data" is used verbatim
+    d.mkdir(parents=True)
+    with open(d / "SYN_dummy_2020.csv", "w") as f:                            # any *dummy*.csv (:60-73)
+        for date, time, ohlc, vol in zip(zc[f"{instr}_csv_date"], zc[f"{instr}_csv_time"], zc[f"{instr}_csv_ohlc"],
+                                         zc[f"{instr}_csv_volume"]):
+            f.write(f"{date.decode()},{time.decode()},{float(ohlc[0])!r},{float(ohlc[1])!r},{float(ohlc[2])!r},{float(ohlc[3])!r},{vol}\n")
+    if how == "env_var":
+        monkeypatch.setenv("FINENVS_DATA_DIR", str(base))
+        name = instr
+    else:
+        name = str(d)
+    env = TimeSeriesEnv(name, "dummy", W, evaluate=bool(z["evaluate"]), device_id=0, obs_dtype=torch.float64, seed=int(z["seed"]))
+    N = len(z["seg_init"])
+    assert env.num_envs == N and env.get_env_args() == {"env_name": name, "num_envs": N, "num_observations": 5,
+                                                       "num_actions": 1, "sequence_length": W}
+    assert np.array_equal(env.env_indices.cpu().numpy(), z["seg_init"])       # incl. the drawn day of the extra env (:253)
+    obs = env.reset()
+    assert obs.shape == (N, W, 5) and obs.dtype == torch.float64
+    np.testing.assert_allclose(obs.cpu().numpy(), z["obs_reset"], rtol=0, atol=1e-12)
+    obs_steps = {int(t): k for k, t in enumerate(z["obs_steps"])}
+    for t in range(z["actions"].shape[0]):
+        o, r, dn, info = env.step(torch.from_numpy(z["actions"][t]).view(N, 1).cuda())
+        assert np.array_equal(dn.cpu().numpy(), z["dones"][t]), t
+        assert np.array_equal(r.cpu().numpy(), z["rewards"][t]), t
+        st = z["states"][t]
+        assert np.array_equal(env.env_indices.cpu().numpy(), st[0].astype(np.int64)), t
+        assert np.array_equal(env.env_pointers.cpu().numpy(), st[1].astype(np.int64)), t
+        assert np.array_equal(env.cash.view(-1).cpu().numpy(), st[2].astype(np.float32)), t
+        assert np.array_equal(env.margin.view(-1).cpu().numpy(), st[5]), t
+        if t in obs_steps:
+            np.testing.assert_allclose(o.cpu().numpy(), z["obs"][obs_steps[t]], rtol=0, atol=1e-12)
+        if "info_steps" in z and t in set(int(x) for x in z["info_steps"]):
+            k = list(z["info_steps"]).index(t)
+            assert np.array_equal(info["returns"].cpu().numpy(), z["info_returns"][k])
