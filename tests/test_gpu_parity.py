@@ -600,3 +600,22 @@ def test_drop_in_constructor_from_csv_replays_the_reference(tmp_path, monkeypatc
         if "info_steps" in z and t in set(int(x) for x in z["info_steps"]):
             k = list(z["info_steps"]).index(t)
             assert np.array_equal(info["returns"].cpu().numpy(), z["info_returns"][k])
+
+
+@pytest.mark.parametrize("dtype,rows", [(torch.float32, 3_300_000), (torch.float64, 1_700_000)])
+def test_pipe_stream_flavour_vs_oracle(dtype, rows):
+    """A log-return table beyond 48 MB switches the pipe variant to its "stream" flavour (cp.async in-ring): both
+    output dtypes against the oracle, ragged last tile included."""
+    from oracle import oracle as orc
+    from finenvs_b200.data import loader
+
+    W, N, bars = 60, 40003, 390
+    rng = np.random.default_rng(rows)
+    prices = np.round(gbm_ohlc(rng, rows, 0.002), 4)
+    seg_start, seg_len = loader.regular_segments(rows, bars, W)
+    series = loader.stage_series(prices, seg_start, seg_len, W, "cuda:0", dtype, keep_logret64=True)
+    env = _env(series, num_envs=N, seed=8, random_reset="all", random_offset=True, obs_dtype=dtype, variant="pipe")
+    assert env.kernel_name().endswith("stream>"), env.kernel_name()
+    fs = orc.series_from_prices(prices, seg_start, seg_len, W, logret=series.logret64.cpu().numpy())
+    ref = orc.OracleEnv(fs, num_envs=N, seed=8, reset_mode=2, random_offset=True, out_f64=dtype == torch.float64)
+    _lockstep(env, ref, 12, np.random.default_rng(1), obs_every=3)
