@@ -100,6 +100,7 @@ def test_parallel_mlp_reproduces_reference_vectors(name):
 @pytest.mark.parametrize("shape,N,E,atol", [((60, 8, 1), 20002, 2, ATOL), ((60, 16, 4, 2), 3000, 0, ATOL), ((60, 1), 4100, 100, ATOL),
                                             ((60, 300, 2), 520, 8, 1e-5),    # 300-term f32 dot products of O(1) terms
                                             ((400, 12, 2), 600, 4, 1e-5),    # > 319 inputs: the generic kernel
+                                            ((400, 64, 2), 300, 2, 1e-5),    # ... with theta too large for shared memory
                                             ((300, 64, 64, 1), 2050, 2, 1e-5)])   # streaming kernel, several chunks per layer
 def test_forward_vs_oracle_large_and_lazy_equals_dense(shape, N, E, atol):
     """Many pairs per warp (persistent loop), eval envs, several chunks per layer, all three forward kernels (fast:
