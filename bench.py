@@ -330,7 +330,11 @@ def main():
                      "traffic": traffic, "peak_source": f"of {peak_src}",
                      "algorithmic_bytes_per_env_step": algorithmic_bytes_per_env_step(W, A),
                      "kernel": env.kernel_name(),
-                     "kernel_ms": kernel_s * 1e3},
+                     "kernel_ms": kernel_s * 1e3,
+                     # what DRAM actually carried (ncu) over the same launch time: when the series is L2-resident the
+                     # window reads never reach DRAM, so `frac` (algorithmic bytes) can exceed 1 while this stays below
+                     "dram_gbs": (traffic / kernel_s / 1e9) if traffic else None,
+                     "dram_frac": (traffic / kernel_s / 1e9 / peak) if traffic else None},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * N * A, "d2h_bytes_per_step": 8 * N,
                 "ms_per_step": e2e_ms / args.steps, "api": "TimeSeriesEnv.step_host -> fe_step_host (pinned host buffers)"},
         "gpu_launches": 2 * args.steps,   # fe_step kernels inside the two timed regions (device + e2e)
