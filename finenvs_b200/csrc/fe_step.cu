@@ -960,11 +960,12 @@ __device__ __forceinline__ float warp_sum32(float v) {
     return v;
 }
 
-// executed by all 32 lanes of warp 0; lane >= A is a neutral asset (no shares, no action, price 1).
-// Per-asset deltas are exchanged through three 32-double scratch rows in shared memory (broadcast LDS, whose
-// addresses do not depend on the cash chain, so the loads run ahead of it); the serial part is only
-// cvt -> DADD -> cvt per asset.  (A first version walked the chain with __shfl_sync inside the loops:
-// ncu showed ~10 k instructions per env in this warp, WARPSYNC.COLLECTIVE wrappers around every shuffle.)
+// executed by all 32 lanes of the env's warp; lane >= A is a neutral asset (no shares, no action, price 1).
+// Cash-independent phases are butterfly sums; for the two greedy entry walks the per-asset costs are exchanged
+// through two 32-double scratch rows in shared memory (broadcast LDS, whose addresses do not depend on the cash
+// chain, so the loads run ahead of it) and the serial part is one DADD + compare per asset.  (A first version walked
+// every phase with __shfl_sync inside the loops: ncu showed ~10 k instructions per env in this warp,
+// WARPSYNC.COLLECTIVE wrappers around every shuffle.)
 template <typename OutT>
 __device__ __forceinline__ void portfolio_step(const FeParams &p, const FeSeries &s, const FeState &st, const Consts &k,
                                                const int64_t i, const int32_t seg_in, const int32_t ptr_in,
@@ -975,7 +976,7 @@ __device__ __forceinline__ void portfolio_step(const FeParams &p, const FeSeries
     const int lane = threadIdx.x & 31;
     const bool act = lane < A;
     const int64_t ia = i * A + lane;
-    double *xa = scratch, *xb = scratch + 32, *xc = scratch + 64; // __syncwarp() orders the exchanges
+    double *xa = scratch, *xb = scratch + 32; // two 32-double rows; __syncwarp() orders the exchanges
     double O = 1.0, H = 1.0, L = 1.0, C = 1.0, margin = 0.0;
     float lng = 0.0f, sht = 0.0f, d = 0.0f;
     if (act) {
@@ -1127,7 +1128,7 @@ fe_portfolio_book_kernel(const FeParams p, const FeSeries s, const FeState st, c
                          const float *__restrict__ actions, OutT *__restrict__ obs, OutT *__restrict__ rewards,
                          int32_t *__restrict__ dones, FeStats *stats, const uint64_t step_arg,
                          const uint64_t *__restrict__ step_dev) {
-    __shared__ double scratch[kBookWarps][96];
+    __shared__ double scratch[kBookWarps][64];
     __shared__ OutT pf_s[kBookWarps][32];
     const uint64_t step = step_dev ? *step_dev : step_arg;
     const int W = p.window, A = p.num_assets;
