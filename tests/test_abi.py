@@ -100,3 +100,31 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("# oracle", ""), f"{f} mentions the oracle"
+
+
+def test_kernel_choice_policy(built):
+    """choose_kernel() (fe_step.cu) through fe_step_kernel_name: a pure host function, so the `auto` policy that
+    DESIGN.md's window sweep justifies is pinned here without a GPU."""
+    L = built.lib()
+
+    def name(N=1 << 20, W=60, A=1, rows=258048, f64=0, variant=built.VARIANT_AUTO):
+        p = built.FeParams(N, 0, N, rows, W, 1024, A, 5, 10000.0, 0.01, 1.5, 0.25, 1, built.RESET_ALL, 1, 0, f64, variant, 0)
+        return L.fe_step_kernel_name(ctypes.byref(p)).decode()
+
+    assert name() == "fe_pipe_kernel<float,cached>"                           # BASELINE config 2
+    assert name(rows=10_000_000) == "fe_pipe_kernel<float,stream>"            # config 4: table larger than L2
+    assert name(f64=1) == "fe_pipe_kernel<double,cached>"
+    assert name(N=1024) == "fe_tile_kernel<float>"                            # config 1: too few tiles per SM
+    assert name(W=4, N=1 << 22) == "fe_tile_kernel<float>" and name(W=16) == "fe_tile_kernel<float>"   # few rows per env
+    assert name(W=24) == "fe_pipe_kernel<float,cached>" and name(W=512, N=1 << 17) == "fe_pipe_kernel<float,cached>"
+    assert name(W=1024, N=1 << 16).startswith("fe_book_kernel + fe_stream_kernel")       # beyond the pipe rings
+    assert name(W=300, f64=1, N=1 << 17).startswith("fe_book_kernel + fe_stream_kernel")  # f64 rings hold 256 rows
+    assert name(W=2000, N=64).startswith("fe_book_kernel + fe_stream_kernel")
+    assert name(A=30, W=128, N=65536).startswith("fe_portfolio_book_kernel + fe_portfolio_stream_kernel")   # config 3
+    assert name(variant=built.VARIANT_TILE) == "fe_tile_kernel<float>"
+    assert name(variant=built.VARIANT_DIRECT) == "fe_direct_kernel<float>"
+    assert name(variant=built.VARIANT_SCATTER) == "fe_scatter_kernel<float>"
+    assert name(variant=built.VARIANT_SPLIT).startswith("fe_book_kernel")
+    assert name(N=64, variant=built.VARIANT_PIPE) == "fe_pipe_kernel<float,cached>"
+    assert name(W=4000, variant=built.VARIANT_TILE).startswith("none")        # does not fit in shared memory
+    assert name(W=4000, variant=built.VARIANT_PIPE).startswith("none")
