@@ -212,7 +212,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"])
     ap.add_argument("--envs", type=int, default=None, help="envs per GPU (default: 1 Mi; c3: 65536)")
     ap.add_argument("--window", type=int, default=None, help="default 60; c3: 128")
-    ap.add_argument("--variant", default="auto", choices=["auto", "tile", "direct", "pipe", "scatter", "split"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "tile", "direct", "pipe", "scatter", "split", "rows"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to its GPU's NUMA-local CPUs")
     args = ap.parse_args()

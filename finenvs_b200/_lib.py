@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FINENVS_B200_LIB") or os.path.join(_HERE, "libfinenvs_b200.so")
 
 RESET_KEEP, RESET_LAST, RESET_ALL = 0, 1, 2
-VARIANT_AUTO, VARIANT_TILE, VARIANT_DIRECT, VARIANT_PORTFOLIO, VARIANT_PIPE, VARIANT_SCATTER, VARIANT_SPLIT = 0, 1, 2, 3, 4, 5, 6
+VARIANT_AUTO, VARIANT_TILE, VARIANT_DIRECT, VARIANT_PORTFOLIO, VARIANT_PIPE, VARIANT_SCATTER, VARIANT_SPLIT, VARIANT_ROWS = 0, 1, 2, 3, 4, 5, 6, 7
 ABI_VERSION = 1
 
 

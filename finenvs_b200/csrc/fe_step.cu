@@ -935,6 +935,116 @@ fe_stream_kernel(const int64_t N, const int W, const OutT *__restrict__ logret, 
 }
 
 // ------------------------------------------------------------------------------------------
+// rows variant (explored alternative, not chosen by `auto`): thread-per-env bookkeeping and warp-autonomous streaming
+// with 16-byte global accesses in ONE launch, no bulk copies, no mbarriers.  A block of 256 threads runs env_step() for
+// 256 envs (headers {row0, position feature} in shared memory), then its 8 warps stream those envs' windows: a WARP
+// owns a group of G consecutive envs (G a power of two >= 4, so a group's slice of the (N, W, 5) tensor starts and ends
+// on a 16-byte boundary for any W) and walks its G*W window rows in chunks of 5120 output bytes: lane l loads rows l,
+// l+32, ... of the chunk (one 16-byte load per f32 row; the env of a row comes from a multiply-high by ceil(2^32 / W),
+// its row0 / position feature by shuffle from the lane holding that env's header), writes them 4 -> 5 interleaved
+// into the warp's PRIVATE 5 KB staging buffer (stride-5 words: conflict-free), and after a __syncwarp the warp copies
+// the buffer out with 16-byte shared loads and 512-contiguous-byte global stores.
+// Measured (profiles/r01_v6_rows_*.txt; c2, 1 Mi envs, W = 60): 0.302 ms (pipe 0.272, tile 0.36, split 0.52) at 3
+// resident blocks per SM (4 blocks / 64 registers: 0.317, spills; 2 blocks: 0.330).  ncu: 81 % of the stall samples sit
+// in the streaming part, on the window loads' scoreboard and on the STG.128 — 24 warps per SM, each a serial
+// load -> stage -> store chain, do not keep enough bytes in flight; c4 (series in HBM): 0.54 ms vs pipe 0.376.
+// ------------------------------------------------------------------------------------------
+constexpr int kRowsThreads = 256;
+constexpr int kRowsWarps = kRowsThreads / 32;
+#ifndef FE_ROWS_MINB
+#define FE_ROWS_MINB 3 /* resident blocks per SM the rows kernel is compiled for (85 registers: no spills) */
+#endif
+constexpr int kRowsChunkBytes = 5120; // staging per warp: 256 f32 rows or 128 f64 rows of 5 values
+template <typename OutT> struct RowsChunk {
+    static constexpr int rows = kRowsChunkBytes / (5 * (int)sizeof(OutT));
+    static constexpr int U = rows / 32; // rows per lane and chunk
+};
+__device__ __forceinline__ int64_t shfl_i64(int64_t v, int src) {
+    const int lo = __shfl_sync(0xFFFFFFFFu, (int)(uint32_t)((uint64_t)v & 0xFFFFFFFFu), src);
+    const int hi = __shfl_sync(0xFFFFFFFFu, (int)(uint32_t)((uint64_t)v >> 32), src);
+    return (int64_t)(((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo);
+}
+// windows of the g <= 32 envs whose headers sit in lanes 0 .. g-1 -> dst (16-byte aligned), through `stage`
+template <typename OutT>
+__device__ __forceinline__ void rows_stream_group(const Row4<OutT> *__restrict__ series_rows, OutT *__restrict__ dst,
+                                                  unsigned char *stage, const int W, const uint32_t magicW, const int g,
+                                                  const int64_t row0_l, const OutT pf_l, const int lane) {
+    constexpr int CH = RowsChunk<OutT>::rows, U = RowsChunk<OutT>::U;
+    const int R = g * W;
+    OutT *so = reinterpret_cast<OutT *>(stage);
+    for (int base = 0; base < R; base += CH) {
+        const int n = min(CH, R - base);
+        Row4<OutT> v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int rl = lane + 32 * u;
+            const int r = rl < n ? base + rl : base; // lanes past the end shuffle along with a valid row
+            const int e = W == 1 ? r : (int)__umulhi((unsigned)r, magicW);
+            const int64_t r0 = shfl_i64(row0_l, e);
+            if (rl < n) v[u] = ldg_row(series_rows + r0 + (r - e * W));
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int rl = lane + 32 * u;
+            const int r = rl < n ? base + rl : base;
+            const OutT pfe = __shfl_sync(0xFFFFFFFFu, pf_l, W == 1 ? r : (int)__umulhi((unsigned)r, magicW));
+            if (rl < n) {
+                OutT *o = so + rl * 5;
+                if constexpr (sizeof(OutT) == 4) {
+                    o[0] = v[u].v.x; o[1] = v[u].v.y; o[2] = v[u].v.z; o[3] = v[u].v.w;
+                } else {
+                    o[0] = v[u].a.x; o[1] = v[u].a.y; o[2] = v[u].b.x; o[3] = v[u].b.y;
+                }
+                o[4] = pfe;
+            }
+        }
+        __syncwarp();
+        OutT *d = dst + (size_t)base * 5;
+        const int nel = n * 5, n16 = (nel * (int)sizeof(OutT)) >> 4;
+        uint4 *d16 = reinterpret_cast<uint4 *>(d);
+        const uint4 *s16 = reinterpret_cast<const uint4 *>(stage);
+#pragma unroll 5
+        for (int i = lane; i < n16; i += 32) d16[i] = s16[i];
+        // only a ragged last group (N % G envs) can end off a 16-byte boundary
+        for (int f = n16 * (16 / (int)sizeof(OutT)) + lane; f < nel; f += 32) d[f] = so[f];
+        __syncwarp();
+    }
+}
+
+template <typename OutT, bool kObserve>
+__global__ void __launch_bounds__(kRowsThreads, FE_ROWS_MINB)
+fe_rows_kernel(const FeParams p, const FeSeries s, const FeState st, const Consts k, const float *__restrict__ actions,
+               OutT *__restrict__ obs, OutT *__restrict__ rewards, int32_t *__restrict__ dones, FeStats *stats,
+               const uint64_t step_arg, const uint64_t *__restrict__ step_dev, const int G, const uint32_t magicW) {
+    __shared__ __align__(16) unsigned char stage_all[kRowsWarps][kRowsChunkBytes];
+    __shared__ int64_t sh_row0[kRowsThreads];
+    __shared__ OutT sh_pf[kRowsThreads];
+    const uint64_t step = step_dev ? *step_dev : step_arg;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t env0 = (int64_t)blockIdx.x * kRowsThreads;
+    const int nvalid = (int)min((int64_t)kRowsThreads, p.num_envs - env0);
+    const bool active = tid < nvalid;
+    EnvResult r;
+    r.done = 0; r.newly_terminated = 0; r.fin_return = 0.0; r.fin_len = 0; r.row0 = 0; r.posfeat = 0.0;
+    if (active) {
+        if (kObserve) r = env_observe(p, s, st, k, env0 + tid);
+        else r = env_step<OutT>(p, s, st, k, env0 + tid, actions, rewards, dones, stats != nullptr, step);
+    }
+    sh_row0[tid] = r.row0;
+    sh_pf[tid] = (OutT)r.posfeat;
+    if (!kObserve) accumulate_stats(stats, r, active);
+    __syncthreads();
+    const size_t n = (size_t)p.window * 5;
+    for (int e = warp * G; e < nvalid; e += kRowsWarps * G) { // G divides 256: groups never straddle blocks
+        const int g = min(G, nvalid - e);
+        const int64_t row0 = lane < g ? sh_row0[e + lane] : 0;
+        const OutT pf = lane < g ? sh_pf[e + lane] : (OutT)0;
+        rows_stream_group<OutT>(reinterpret_cast<const Row4<OutT> *>(s.logret), obs + (size_t)(env0 + e) * n, stage_all[warp],
+                                p.window, magicW, g, row0, pf, lane);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // portfolio variant (A > 1 assets, one cash account): EXTENSION, the reference is single-asset (:223).
 // Semantics: the reference's phases in the reference's order; inside a phase the
 // cash moves ONCE: by the f64 butterfly sum of the per-asset deltas where these do not depend on cash (sales,
@@ -1398,7 +1508,7 @@ int pick_pipe_stages(const FeParams &p, bool f64) {
 // W = 4 / 16: tile 0.19 / 0.24 ms vs pipe 0.73 / 0.37 ms — with so few rows per env the 6 bookkeeper warps are the
 // bottleneck, while the tile variant gives every env its own thread; W = 60 / 128 / 390: pipe 0.27 / 0.27 / 0.23 vs tile
 // 0.36 / 0.38 / 0.29); else tile while the window fits in shared memory; else direct.
-enum StepKernel { K_PORTFOLIO, K_SPLIT, K_SCATTER, K_PIPE, K_TILE, K_DIRECT, K_ERR_SMEM };
+enum StepKernel { K_PORTFOLIO, K_SPLIT, K_ROWS, K_SCATTER, K_PIPE, K_TILE, K_DIRECT, K_ERR_SMEM };
 struct StepChoice {
     StepKernel kern;
     int te;      // envs per tile (pipe / scatter / tile)
@@ -1411,6 +1521,8 @@ StepChoice choose_kernel(const FeParams &p, bool f64) {
     if (p.num_assets > 1 || p.variant == FE_VARIANT_PORTFOLIO) { c.kern = K_PORTFOLIO; return c; }
     static const int auto_split = env_override("FE_AUTO_SPLIT");     // sweeps: 1 = "auto" prefers split, -1 = never
     if ((p.variant == FE_VARIANT_SPLIT || (p.variant == FE_VARIANT_AUTO && auto_split > 0))) { c.kern = K_SPLIT; return c; }
+    // rows: the multiply-high row -> env map is exact while 32 * W * W < 2^32
+    if (p.variant == FE_VARIANT_ROWS) { c.kern = p.window <= 8192 ? K_ROWS : K_ERR_SMEM; return c; }
     static const int auto_scatter = env_override("FE_AUTO_SCATTER"); // sweeps: 1 = "auto" prefers scatter
     static const int no_pipe = env_override("FE_NO_PIPE");           // sweeps: "auto" never picks pipe
     // small populations: a persistent grid needs a few tiles per SM to hide its prologue
@@ -1497,6 +1609,22 @@ int launch(const FeParams &p, const FeSeries &s, const FeState &st, const float 
         const int64_t need = (p.num_envs * 32 + kStreamThreads - 1) / kStreamThreads;
         if (blocks > need) blocks = need;
         fe_stream_kernel<OutT><<<(unsigned)blocks, kStreamThreads, 0, stream>>>(p.num_envs, p.window, (const OutT *)s.logret, (OutT *)obs);
+        break;
+    }
+    case K_ROWS: {
+        if ((uintptr_t)obs & 15) return FE_EALIGN;
+        int G = 4; // envs per warp group: a power of two (divides the block's 256 envs), >= 256 rows when it can
+        while (G < 32 && G * p.window < 256) G *= 2;
+        const uint32_t magicW = p.window == 1 ? 0u : (uint32_t)((((uint64_t)1 << 32) + p.window - 1) / p.window);
+        auto kern = fe_rows_kernel<OutT, kObserve>;
+        static bool configured[16] = {false};
+        if (!configured[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (e != cudaSuccess) return (int)e;
+            configured[dev] = true;
+        }
+        kern<<<(unsigned)((p.num_envs + kRowsThreads - 1) / kRowsThreads), kRowsThreads, 0, stream>>>(
+            p, s, st, k, actions, (OutT *)obs, (OutT *)rewards, dones, stats, step, step_dev, G, magicW);
         break;
     }
     case K_SCATTER: {
@@ -1626,6 +1754,7 @@ const char *fe_step_kernel_name(const FeParams *p) {
     case K_PORTFOLIO:
         return f64 ? "fe_portfolio_book_kernel + fe_portfolio_stream_kernel<double>" : "fe_portfolio_book_kernel + fe_portfolio_stream_kernel<float>";
     case K_SPLIT: return f64 ? "fe_book_kernel + fe_stream_kernel<double>" : "fe_book_kernel + fe_stream_kernel<float>";
+    case K_ROWS: return f64 ? "fe_rows_kernel<double>" : "fe_rows_kernel<float>";
     case K_SCATTER: return f64 ? "fe_scatter_kernel<double>" : "fe_scatter_kernel<float>";
     case K_PIPE:
         return c.sin == 0 ? (f64 ? "fe_pipe_kernel<double,cached>" : "fe_pipe_kernel<float,cached>")

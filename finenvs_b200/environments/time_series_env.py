@@ -35,7 +35,8 @@ except Exception:  # pragma: no cover - gym is not installed in the target image
 
 _RESET_MODES = {"keep": _lib.RESET_KEEP, "last": _lib.RESET_LAST, "all": _lib.RESET_ALL}
 _VARIANTS = {"auto": _lib.VARIANT_AUTO, "tile": _lib.VARIANT_TILE, "direct": _lib.VARIANT_DIRECT,
-             "portfolio": _lib.VARIANT_PORTFOLIO, "pipe": _lib.VARIANT_PIPE, "scatter": _lib.VARIANT_SCATTER, "split": _lib.VARIANT_SPLIT}
+             "portfolio": _lib.VARIANT_PORTFOLIO, "pipe": _lib.VARIANT_PIPE, "scatter": _lib.VARIANT_SCATTER, "split": _lib.VARIANT_SPLIT,
+             "rows": _lib.VARIANT_ROWS}
 
 
 class LazyObs:
@@ -178,7 +179,7 @@ class TimeSeriesEnv(BaseObject):
                       population (multi-GPU); draws are keyed by global id, so results do not
                       depend on the sharding.
         track_stats   accumulate episode count / return / length on the device (stats()).
-        variant       "auto" | "pipe" | "tile" | "direct" | "scatter" | "portfolio" kernel variant (auto: pipe for
+        variant       "auto" | "pipe" | "tile" | "direct" | "scatter" | "split" | "rows" | "portfolio" kernel variant (auto: pipe for
                       populations of >= 18 944 envs with windows of >= 24 rows, else tile; direct when the window does
                       not fit in shared memory; portfolio whenever the series has more than one asset).
         flat_obs      return observations as (N, W*num_obs) — the 2-D input the ES agent's ParallelMLP needs

@@ -43,6 +43,7 @@ extern "C" {
 #define FE_VARIANT_PIPE 4  /* persistent warp-specialised pipeline (bookkeeper / mover warps, multi-stage rings) */
 #define FE_VARIANT_SPLIT 6   /* two launches: thread-per-env bookkeeping, then warp-per-env streaming with fully coalesced stores */
 #define FE_VARIANT_SCATTER 5 /* persistent pipeline whose window elements land in the output tile by element-sized cp.async (no register staging) */
+#define FE_VARIANT_ROWS 7    /* one launch: thread-per-env bookkeeping, then warp-autonomous streaming through private staging with 16-byte global loads / stores */
 #define FE_VARIANT_PORTFOLIO 3 /* warp-per-env bookkeeping kernel + block-per-env streaming kernel; always used when num_assets > 1 */
 
 typedef struct FeParams {

@@ -125,6 +125,8 @@ def test_kernel_choice_policy(built):
     assert name(variant=built.VARIANT_DIRECT) == "fe_direct_kernel<float>"
     assert name(variant=built.VARIANT_SCATTER) == "fe_scatter_kernel<float>"
     assert name(variant=built.VARIANT_SPLIT).startswith("fe_book_kernel")
+    assert name(variant=built.VARIANT_ROWS) == "fe_rows_kernel<float>"
+    assert name(W=9000, variant=built.VARIANT_ROWS).startswith("none")       # row -> env multiply-high no longer exact
     assert name(N=64, variant=built.VARIANT_PIPE) == "fe_pipe_kernel<float,cached>"
     assert name(W=4000, variant=built.VARIANT_TILE).startswith("none")        # does not fit in shared memory
     assert name(W=4000, variant=built.VARIANT_PIPE).startswith("none")

@@ -32,7 +32,8 @@ def _env(series, **kw):
                                            (torch.float64, "portfolio"), (torch.float32, "pipe"),
                                            (torch.float64, "pipe"), (torch.float32, "scatter"),
                                            (torch.float64, "scatter"), (torch.float32, "split"),
-                                           (torch.float64, "split")])
+                                           (torch.float64, "split"), (torch.float32, "rows"),
+                                           (torch.float64, "rows")])
 def test_cuda_replays_reference_trace(name, dtype, variant):
     z = load_trace(name)
     if variant == "pipe" and _lib_mod().lib().fe_pipe_envs(int(z["window"]), int(dtype == torch.float64), 0) == 0:
@@ -463,7 +464,7 @@ def test_flat_obs_and_es_env_args():
     assert o0.shape == (500, W * 5) and int(b._ptr.abs().sum()) == 0 and float(b._cash.min()) == 10000.0
 
 
-@pytest.mark.parametrize("variant", ["pipe", "scatter", "split"])
+@pytest.mark.parametrize("variant", ["pipe", "scatter", "split", "rows"])
 @pytest.mark.parametrize("W,N,dtype", [(60, 1024, torch.float32), (60, 5003, torch.float32), (60, 4099, torch.float64),
                                        (8, 70001, torch.float32), (128, 3000, torch.float32), (3, 999, torch.float32)])
 def test_pipe_variant_vs_oracle(W, N, dtype, variant):
@@ -511,7 +512,7 @@ def test_step_host_pipeline_equals_device_step(N, A, dtype):
     assert int(sa["n_done"]) == int(sb["n_done"]) > 0 and int(sa["sum_len"]) == int(sb["sum_len"])
 
 
-@pytest.mark.parametrize("variant,A,N", [("tile", 1, 3001), ("pipe", 1, 40000), ("split", 1, 5003), ("auto", 3, 2500)])
+@pytest.mark.parametrize("variant,A,N", [("tile", 1, 3001), ("pipe", 1, 40000), ("split", 1, 5003), ("rows", 1, 5003), ("auto", 3, 2500)])
 @pytest.mark.parametrize("params", [(40, 500.0, 0.37, 2.25, 0.4), (1, 250000.0, 0.0, 1.0, 0.1), (12, 20000.0, 0.05, 1.2, 0.3)])
 def test_non_default_parameters_vs_oracle(variant, A, N, params):
     """Every constructor parameter of the reference off its default (time_series_env.py:20-26; the three golden
