@@ -27,7 +27,7 @@ for W in (5, 60):
     firsts = W + bars * np.arange(days)
     for dtype in (torch.float32, torch.float64):
         series = loader.stage_series(prices, firsts - W, np.full(days, W + bars, np.int32), W, "cuda:0", dtype)
-        for variant in ("tile", "direct", "pipe", "scatter", "split"):
+        for variant in ("tile", "direct", "pipe", "scatter", "split", "rows"):
             for kw in (dict(random_reset="all", random_offset=True, track_stats=True), dict(evaluate=True)):
                 env = TimeSeriesEnv("san", num_intervals=W, series=series, num_envs=None if "evaluate" in kw else 203,
                                     seed=1, obs_dtype=dtype, variant=variant, **kw)
