@@ -337,7 +337,9 @@ def main():
                      "dram_frac": (traffic / kernel_s / 1e9 / peak) if traffic else None},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * N * A, "d2h_bytes_per_step": 8 * N,
                 "ms_per_step": e2e_ms / args.steps, "api": "TimeSeriesEnv.step_host -> fe_step_host (pinned host buffers)"},
-        "gpu_launches": 2 * args.steps,   # fe_step kernels inside the two timed regions (device + e2e)
+        # kernels of this library inside the two timed regions (device + e2e legs): one per step, two where the step is
+        # a bookkeeping + a streaming launch (portfolio, split); with pinned buffers the host step is the same launch(es)
+        "gpu_launches": 2 * args.steps * (2 if " + " in env.kernel_name() else 1),
         "clocks": sampler.summary(),
         "episodes_finished_last_step": n_done,
     }
