@@ -73,7 +73,7 @@ def test_widened_adversarial_series(tmp_path):
     assert _lockstep(p, 6, 250, seed=23, widen=64, action_fn=act) > 500
 
 
-@pytest.mark.parametrize("case", range(10))
+@pytest.mark.parametrize("case", range(40))
 def test_fuzzed_series_and_parameters(tmp_path, case):
     """Seeded fuzz: ragged days (1-bar and short days included), volatility from calm to violent, every constructor
     parameter of the reference moved off its default (time_series_env.py:15-29), both modes — bit for bit."""
