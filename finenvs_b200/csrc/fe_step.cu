@@ -1733,6 +1733,8 @@ const char *fe_error_string(int code) {
     case FE_EINVAL: return "finenvs_b200: invalid argument (null pointer, non-positive size or num_assets outside 1..32)";
     case FE_EALIGN: return "finenvs_b200: pointer not 16-byte aligned";
     case FE_ESMEM: return "finenvs_b200: window too large for the tile variant";
+    case FE_EIO: return "finenvs_b200: cannot open or map the file";
+    case FE_ECSV: return "finenvs_b200: CSV record outside the format of the native reader";
     default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "finenvs_b200: unknown error";
     }
 }

@@ -97,16 +97,55 @@ def segment_table(dates: np.ndarray, window: int):
     return start[keep], (last[keep] - start[keep] + 1).astype(np.int32)
 
 
-def read_market_csv(path: str, window: int) -> HostSeries:
-    """read_data :80-88 + force_market_hours :90-91 + determine_environment_bounds :127-152."""
+FE_ECSV = -5   # include/finenvs_b200.h: a record outside the native reader's format
+
+
+def read_csv_native(path: str, num_threads: int = 0):
+    """The CSV through the library's memory-mapped multi-threaded reader (csrc/fe_csv.cu, fe_csv_open / fe_csv_read):
+    (date_key (T,) i64, sec_of_day (T,) i32, ohlc (T, 4) f64), prices bit-identical to pandas.read_csv's, or None when
+    the file uses CSV syntax the native reader does not handle (quotes, header lines, missing values, other time formats)."""
+    import ctypes as C
+
+    L = _lib.lib()
+    handle, rows = C.c_void_p(), C.c_int64()
+    _lib.check(L.fe_csv_open(os.fsencode(path), num_threads, C.byref(handle), C.byref(rows)), f"fe_csv_open({path})")
+    try:
+        T = rows.value
+        date_key = np.empty(T, np.int64)
+        secs = np.empty(T, np.int32)
+        ohlc = np.empty((T, 4), np.float64)
+        rc = L.fe_csv_read(handle, date_key.ctypes.data, secs.ctypes.data, ohlc.ctypes.data)
+    finally:
+        L.fe_csv_close(handle)
+    if rc == FE_ECSV:
+        return None
+    _lib.check(rc, "fe_csv_read")
+    return date_key, secs, ohlc
+
+
+def read_csv_pandas(path: str):
+    """The reference's own reader (:80-88): same three arrays as read_csv_native, dates as strings."""
     import pandas as pd
 
     df = pd.read_csv(path, names=["Date", "Time", "Open", "High", "Low", "Close", "Volume"])
-    secs = _seconds_of_day(df["Time"])
+    return (df["Date"].to_numpy(), _seconds_of_day(df["Time"]),
+            np.ascontiguousarray(df[["Open", "High", "Low", "Close"]].to_numpy(dtype=np.float64)))
+
+
+def read_market_csv(path: str, window: int, reader: str = "auto") -> HostSeries:
+    """read_data :80-88 + force_market_hours :90-91 + determine_environment_bounds :127-152.
+    reader: "native" (fe_csv_*; raises on syntax it does not handle), "pandas", or "auto" (native, pandas for such files)."""
+    if reader not in ("auto", "native", "pandas"):
+        raise ValueError("reader must be 'auto', 'native' or 'pandas'")
+    cols = read_csv_native(path) if reader != "pandas" else None
+    if cols is None:
+        if reader == "native":
+            raise Exception(f"{path}: CSV syntax outside the native reader's format (use reader='pandas')")
+        cols = read_csv_pandas(path)
+    dates, secs, ohlc = cols
     keep = (secs >= MARKET_OPEN_S) & (secs <= MARKET_CLOSE_S)
-    df = df[keep]
-    prices = np.ascontiguousarray(df[["Open", "High", "Low", "Close"]].to_numpy(dtype=np.float64))
-    seg_start, seg_len_raw = segment_table(df["Date"].to_numpy(), window)
+    prices = np.ascontiguousarray(ohlc[keep])
+    seg_start, seg_len_raw = segment_table(dates[keep], window)
     if len(seg_start) == 0:
         raise Exception(f"{path}: no trading day has {window} bars of history before it")
     return HostSeries(prices, seg_start, seg_len_raw)

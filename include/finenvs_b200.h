@@ -30,6 +30,8 @@ extern "C" {
 #define FE_EINVAL (-1)   /* null pointer / non-positive size / unsupported num_assets */
 #define FE_EALIGN (-2)   /* pointer not 16-byte aligned */
 #define FE_ESMEM (-3)    /* window too large for the requested kernel variant */
+#define FE_EIO (-4)      /* fe_csv_open: the file cannot be opened or mapped */
+#define FE_ECSV (-5)     /* fe_csv_read: a record is outside the format the native reader handles (the caller falls back to pandas) */
 
 /* FeParams.reset_mode */
 #define FE_RESET_KEEP 0  /* finished envs restart on the same segment (reference evaluate=True, :504) */
@@ -170,6 +172,17 @@ int fe_reset_all(const FeParams *p, const FeSeries *s, const FeState *st, uint64
 /* The redraw RNG evaluated on the host (Philox4x32-10; key = seed, counter = (env id, step, kind)):
  * lets callers reproduce / pre-compute draws.  kind: 0 step-time reset, 1 reset_all / constructor. */
 void fe_philox(uint64_t seed, uint64_t env_id, uint64_t step, uint32_t kind, uint32_t out[4]);
+
+/* Market-data CSV reader of the loader (host code, no GPU work): replaces pandas.read_csv of read_data()
+ * (finenvs/environments/time_series_env.py:80-88) for records `Date,Time,Open,High,Low,Close,Volume`.
+ * fe_csv_open maps the file, cuts it into one chunk per thread (num_threads <= 0: all hardware threads) and counts the
+ * records (non-empty lines); fe_csv_read fills caller-owned arrays of num_rows entries: date_key = 64-bit FNV-1a hash of
+ * the Date string (the reference compares dates as strings, :98, :141-152), sec_of_day = seconds since midnight of the
+ * Time field (for between_time("9:30", "15:59"), :90-91), ohlc = (num_rows, 4) float64 converted exactly like pandas'
+ * default converter (bit-identical prices).  FE_ECSV = some record is outside this format.  fe_csv_close unmaps. */
+int fe_csv_open(const char *path, int32_t num_threads, void **handle, int64_t *num_rows);
+int fe_csv_read(void *handle, int64_t *date_key, int32_t *sec_of_day, double *ohlc);
+void fe_csv_close(void *handle);
 
 /* ---- callers of the step --------------------------------------------------------------- */
 

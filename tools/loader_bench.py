@@ -49,6 +49,7 @@ def main():
     ap.add_argument("--bars", type=int, default=390)
     ap.add_argument("--window", type=int, default=60)
     ap.add_argument("--stage-rows", type=int, default=0)
+    ap.add_argument("--no-reference", action="store_true", help="skip the reference constructor (O(days x rows): hours for millions of rows)")
     args = ap.parse_args()
     from finenvs_b200.data import loader
 
@@ -62,14 +63,18 @@ def main():
         import pandas  # noqa: F401  (not part of the timed region, as for the reference below)
 
         t0 = time.perf_counter()
-        host = loader.read_market_csv(path, args.window)
+        host = loader.read_market_csv(path, args.window)            # native reader (csrc/fe_csv.cu), all host threads
         out["loader_read_market_csv_s"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        loader.read_market_csv(path, args.window, reader="pandas")  # the same loader on pandas.read_csv
+        out["loader_read_market_csv_pandas_s"] = time.perf_counter() - t0
+        out["host_threads"] = os.cpu_count()
         out["segments"] = int(len(host.seg_start))
         out["rows"] = int(host.prices.shape[0])
         try:
             from oracle import ref_harness
 
-            if ref_harness.available():
+            if ref_harness.available() and not args.no_reference:
                 mod = ref_harness.ref_module()
                 t0 = time.perf_counter()
                 env = mod.TimeSeriesEnv(sub, "dummy", num_intervals=args.window, device_id=-1)
