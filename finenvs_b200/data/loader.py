@@ -79,19 +79,37 @@ def _seconds_of_day(times) -> np.ndarray:
     return secs.to_numpy()[codes]
 
 
-def segment_table(dates: np.ndarray, window: int):
-    """First/last row of every distinct Date (:141-152), backtracked by W rows of history; days
-    whose history would start before row 0 are skipped (:134).  Order = first appearance.  One hash pass over the
-    rows (the reference scans the whole frame once per day)."""
+def _first_last_rows(dates: np.ndarray):
+    """First and last row of every distinct value of `dates`, in order of first appearance."""
+    n = len(dates)
+    if n == 0:
+        return np.zeros(0, np.int64), np.zeros(0, np.int64)
+    if dates.dtype.kind in "iu":
+        # integer keys (the native reader's date hashes): days are runs of equal keys; one comparison pass finds them
+        starts = np.flatnonzero(np.concatenate(([True], dates[1:] != dates[:-1])))
+        if len(np.unique(dates[starts])) == len(starts):       # every day is ONE run (any normal file)
+            return starts.astype(np.int64), np.concatenate((starts[1:] - 1, [n - 1])).astype(np.int64)
+        _, first, inv = np.unique(dates, return_index=True, return_inverse=True)   # a date that comes back later
+        last = np.zeros(len(first), np.int64)
+        np.maximum.at(last, inv, np.arange(n, dtype=np.int64))
+        order = np.argsort(first, kind="stable")
+        return first[order].astype(np.int64), last[order]
     import pandas as pd
 
     inv, uniques = pd.factorize(dates)          # codes in order of first appearance
-    n = len(uniques)
-    idx = np.arange(len(dates), dtype=np.int64)
-    first = np.full(n, len(dates), dtype=np.int64)
-    last = np.zeros(n, dtype=np.int64)
+    idx = np.arange(n, dtype=np.int64)
+    first = np.full(len(uniques), n, dtype=np.int64)
+    last = np.zeros(len(uniques), dtype=np.int64)
     np.minimum.at(first, inv, idx)
     np.maximum.at(last, inv, idx)
+    return first, last
+
+
+def segment_table(dates: np.ndarray, window: int):
+    """First/last row of every distinct Date (:141-152), backtracked by W rows of history; days
+    whose history would start before row 0 are skipped (:134).  Order = first appearance.  One pass over the
+    rows (the reference scans the whole frame once per day)."""
+    first, last = _first_last_rows(np.asarray(dates))
     start = first - window
     keep = start >= 0
     return start[keep], (last[keep] - start[keep] + 1).astype(np.int32)

@@ -79,5 +79,13 @@ def test_segment_table_edge_cases():
     assert start.tolist() == [4, 5] and length.tolist() == [5, 8]
     start, length = loader.segment_table(dates, 1)
     assert start.tolist() == [2, 7, 8] and length.tolist() == [6, 2, 5]
+    # integer keys (the native reader's date hashes): same tables, also when a date comes back after another one
+    keys = np.array([7] * 3 + [-2] * 5 + [99] * 1 + [4] * 4, np.int64)
+    assert [a.tolist() for a in loader.segment_table(keys, 4)] == [[4, 5], [5, 8]]
+    back = np.array(["a", "a", "b", "b", "b", "a", "c", "c"])
+    codes = np.array([hash(x) for x in back], np.int64)
+    for w in (1, 2):
+        assert [a.tolist() for a in loader.segment_table(codes, w)] == [a.tolist() for a in loader.segment_table(back, w)]
+    assert [a.tolist() for a in loader.segment_table(np.zeros(0, np.int64), 3)] == [[], []]
     s, n = loader.regular_segments(1000, 100, 60)
     assert s.tolist() == [40 + 100 * i for i in range(9)] and (n == 160).all()
