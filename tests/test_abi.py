@@ -130,3 +130,36 @@ def test_kernel_choice_policy(built):
     assert name(N=64, variant=built.VARIANT_PIPE) == "fe_pipe_kernel<float,cached>"
     assert name(W=4000, variant=built.VARIANT_TILE).startswith("none")        # does not fit in shared memory
     assert name(W=4000, variant=built.VARIANT_PIPE).startswith("none")
+
+
+def test_header_is_plain_c_and_a_c_program_links_against_the_library(built, tmp_path):
+    """include/finenvs_b200.h is what a non-Python embedder binds: it must compile as C99, the struct
+    sizes a C compiler sees must be the ones the ctypes mirror uses, and a C program must link and call the library."""
+    import shutil
+    import subprocess
+
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "finenvs_b200.h"\n'
+        "int main(void) {\n"
+        '  printf("%d %zu %zu %zu %zu %zu\\n", fe_version(), sizeof(FeParams), sizeof(FeSeries), sizeof(FeState),\n'
+        "         sizeof(FeStats), sizeof(FeEsNet));\n"
+        '  printf("%s\\n", fe_error_string(FE_ECSV));\n'
+        "  void *h = 0; int64_t rows = -1;\n"
+        '  printf("%d\\n", fe_csv_open("/nonexistent/x.csv", 1, &h, &rows));\n'
+        "  return fe_step(0, 0, 0, 0, 0, 0, 0, 0, 1, 0) == FE_EINVAL ? 0 : 1;\n}\n")
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(built.LIB_PATH)
+    subprocess.check_call([cc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-l:" + os.path.basename(built.LIB_PATH), "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    l1, l2, l3 = out.stdout.splitlines()
+    ver, sp, ss, sst, sstat, snet = (int(x) for x in l1.split())
+    assert ver == built.ABI_VERSION
+    assert (sp, ss, sst) == (ctypes.sizeof(built.FeParams), ctypes.sizeof(built.FeSeries), ctypes.sizeof(built.FeState))
+    assert sstat == built.STATS_BYTES and snet == ctypes.sizeof(built.FeEsNet)
+    assert "CSV" in l2 and int(l3) == -4
