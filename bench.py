@@ -1,22 +1,34 @@
 #!/usr/bin/env python
 """bench.py — env-steps/s of the fused trading-env step kernel (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4]
 
-A "step" is one pass of the hot path over one batch of envs: one fe_step launch over this GPU's
-envs.  Default workload = BASELINE config 2 (single asset, 1 Mi envs per GPU, W=60, synthetic GBM
-daily bars); `--workload c4` swaps in the 10 M-row minute-bar series (bigger than L2).  N>1 is
-launched by torchrun, one rank per GPU; envs are sharded (weak scaling: 1 Mi envs per GPU), the
+A "step" is one pass of the hot path over one batch of envs: one fe_step launch over this GPU's envs.
+Default workload = BASELINE config 2 (single asset, 1 Mi envs per GPU, W=60, synthetic GBM daily bars).
+N>1 is launched by torchrun, one rank per GPU; envs are sharded (weak scaling: 1 Mi envs per GPU), the
 series is replicated, the step needs no collective.  Rank 0 prints ONE JSON line.
 
-value  = device-resident throughput (actions already in HBM), CUDA events, max over ranks.
-e2e    = same metric through the host-buffer C-ABI call fe_step_host (TimeSeriesEnv.step_host):
-         per step 4N bytes of actions pinned-host -> HBM and 8N bytes (rewards f32 + dones i32)
-         HBM -> pinned host; the observation stays in HBM for the policy.
-roofline = algorithmic bytes per launch (2264 B per env-step at A=1, W=60, f32 obs)
-         / average launch duration, against MEASURED_PEAKS.json hbm_gbs.
-cpu_baseline / --impl reference = the CPU oracle (a C port of the reference's algorithm; the
-         reference itself is torch-eager Python and cannot travel to the GPU box) on all host threads.
+Timing: W warm-up steps, then the K-step block is timed `blocks` times back to back (CUDA events on the
+launch stream, barrier + synchronize around every block, max over ranks per block); `value` / `ms_per_step`
+come from the MEDIAN block, `timing` also gives min and max — a 20-step block is 5 ms, one block alone is
+at the mercy of a clock ramp.
+
+value    = device-resident throughput through TimeSeriesEnv.step_into (caller-owned outputs, actions in HBM).
+public_step = the same loop through the drop-in call TimeSeriesEnv.step(actions) (allocates obs/rewards/dones).
+e2e      = the same metric through the host-buffer C-ABI call fe_step_host (TimeSeriesEnv.step_host): per step
+           4N bytes of actions pinned-host -> HBM and 8N bytes (rewards f32 + dones i32) HBM -> pinned host; the
+           observation stays in HBM for the policy.
+roofline = bytes that must cross DRAM per launch / average launch duration, against MEASURED_PEAKS.json hbm_gbs:
+           the algorithmic bytes (2264 B per env-step at A=1, W=60, f32 obs) MINUS the window reads when
+           the log-return table is L2-resident (c2, c3: those reads never reach DRAM, so counting them gave a
+           "fraction" above 1); the full algorithmic figure stays beside it as `algorithmic_*`, and the ncu-measured
+           DRAM traffic of the same launch as `traffic` / `dram_frac`.
+also     = the other BASELINE workloads measured in the same process (N=1: c4 and c3; N>1: c4), same protocol.
+collectives (N>1) = device time of the NCCL collectives the path uses outside the step (episode statistics
+           all-reduce, ES fitness all-gather, ES gradient all-reduce).
+cpu_baseline / --impl reference = the reference's OWN TimeSeriesEnv.step (unmodified, from baseline/_ref,
+           device_id=-1) on the box's host cores, thread count forced; the C/OpenMP oracle port is reported
+           beside it as `cpu_port`.
 """
 from __future__ import annotations
 
@@ -37,6 +49,7 @@ METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
 SERIES_SEED = 20260101
 ACTION_SEED = 1234
+L2_RESIDENT_BYTES = 48 << 20   # the library's own threshold for the "cached" flavour (fe_step.cu: pick_pipe_stages)
 
 
 # ------------------------------------------------------------------------------ workloads ----
@@ -52,16 +65,28 @@ def algorithmic_bytes_per_env_step(W: int, A: int = 1, obs_bytes: int = 4) -> in
     return window_read + obs_write + ohlc + cash + per_asset_state + pointer + tables + 4 * A + obs_bytes + 4
 
 
+def window_read_bytes(W: int, A: int = 1, obs_bytes: int = 4) -> int:
+    return W * 4 * A * obs_bytes
+
+
+WORKLOAD_ASSETS = {"c2": 1, "c4": 1, "c3": 30}
+WORKLOAD_DEFAULTS = {"c2": (1 << 20, 60), "c4": (1 << 20, 60), "c3": (65536, 128)}   # (envs per GPU, window)
+WORKLOAD_SERIES = {"c2": (1024 * 252, 252, 0.01), "c3": (1024 * 252, 252, 0.01), "c4": (10_000_000, 390, 0.0005)}
+
+WORKLOAD_NAMES = {
+    "c3": "30-asset portfolio-allocation env, 65536 envs, 128-step window, transaction costs, 1 B200",
+    "c2": "single-asset env, 1M envs, 60-step window, fused step kernel on 1 B200 vs reference",
+    "c4": "synthetic minute-bar series of 10M timesteps, 1M envs per GPU with random start offsets, env-sharded",
+}
+
+
 def make_series(workload: str, W: int):
     """Synthetic GBM OHLC (SURVEY.md §8d recipe) + segment table."""
     from finenvs_b200.data import loader
     from parity_utils import gbm_ohlc
 
     rng = np.random.default_rng(SERIES_SEED)
-    if workload == "c4":     # minute bars, 10 M rows, 390-bar segments
-        T, bars, sigma = 10_000_000, 390, 0.0005
-    else:                    # c2 / c1 / c3: daily bars, 1024 segments x 252 bars
-        T, bars, sigma = 1024 * 252, 252, 0.01
+    T, bars, sigma = WORKLOAD_SERIES[workload]
     if workload == "c3":     # 30 independent GBM assets, time-major (T, A, 4)
         prices = np.stack([np.round(gbm_ohlc(rng, T, sigma, s0=20.0 + 7 * a), 4) for a in range(WORKLOAD_ASSETS["c3"])], axis=1)
     else:
@@ -70,14 +95,13 @@ def make_series(workload: str, W: int):
     return prices, seg_start, seg_len, {"rows": T, "bars_per_segment": bars, "sigma": sigma}
 
 
-WORKLOAD_ASSETS = {"c2": 1, "c4": 1, "c3": 30}
-WORKLOAD_DEFAULTS = {"c2": (1 << 20, 60), "c4": (1 << 20, 60), "c3": (65536, 128)}   # (envs per GPU, window)
-
-WORKLOAD_NAMES = {
-    "c3": "30-asset portfolio-allocation env, 65536 envs, 128-step window, transaction costs, 1 B200",
-    "c2": "single-asset env, 1M envs, 60-step window, fused step kernel on 1 B200 vs reference",
-    "c4": "synthetic minute-bar series of 10M timesteps, 1M envs per GPU with random start offsets, env-sharded",
-}
+def workload_config(workload: str, envs: int, window: int, world: int):
+    return {"workload": WORKLOAD_NAMES[workload], "envs_per_gpu": envs, "total_envs": envs * world,
+            "window": window, "assets": WORKLOAD_ASSETS[workload], "obs_dtype": "float32",
+            "reset": "all envs redraw (segment, offset), Philox",
+            "parallelism": f"env-sharded x{world}, series replicated, no per-step collective",
+            "l2": "per-step working set (obs >= 1.2 GB + state) >> 126 MB L2: no flush needed",
+            **dict(zip(("rows", "bars_per_segment", "sigma"), WORKLOAD_SERIES[workload]))}
 
 
 # ------------------------------------------------------------------------------ clocks -------
@@ -139,15 +163,42 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------ CPU legs -----
-def cpu_oracle_throughput(W: int, workload: str, sample_envs: int, steps: int, warmup: int, budget_s: float | None):
-    """The oracle port stepped on all host threads over a bounded sample of the workload.
-    Returns (env-steps/s, seconds per step, threads, steps timed)."""
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def force_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU legs must use the cores the box has.  Call before torch / the
+    oracle library initialise their OpenMP runtimes (and set them explicitly afterwards as well)."""
+    n = str(host_threads())
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[k] = n
+
+
+def cpu_model() -> str:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def cpu_port_throughput(W: int, workload: str, sample_envs: int, steps: int, warmup: int, budget_s: float | None):
+    """The oracle port (oracle/fe_oracle.c, the reference's algorithm restated in C + OpenMP) stepped on all host
+    threads over a bounded sample of the workload.  Returns (env-steps/s, seconds per step, threads, steps timed)."""
     from oracle import oracle as orc
 
     prices, seg_start, seg_len, _ = make_series(workload, W)
     fs = orc.series_from_prices(prices, seg_start, seg_len, W)
     env = orc.OracleEnv(fs, num_envs=sample_envs, seed=ACTION_SEED, reset_mode=orc.RESET_ALL, random_offset=True,
                         out_f64=False)
+    orc.lib().feo_set_num_threads(host_threads())
     threads = orc.lib().feo_num_threads()
     rng = np.random.default_rng(ACTION_SEED)
     A = WORKLOAD_ASSETS[workload]
@@ -176,33 +227,317 @@ def cpu_oracle_throughput(W: int, workload: str, sample_envs: int, steps: int, w
     return sample_envs * done_steps / dt, dt / done_steps, threads, done_steps
 
 
+class ReferenceRunner:
+    """The UNMODIFIED reference env (baseline/_ref, finenvs/environments/time_series_env.py:14-536) on the host cores.
+
+    Inputs = BASELINE config 1 as SURVEY §8d restates it: the c2 GBM daily-bar series written as a reference-format
+    CSV (1024 dates x 252 one-minute-labelled bars), W=60 => D=1023 days, N=1024 envs natively; widened to more envs by
+    re-assigning the state tensors exactly as SURVEY App. C.4 does (env i on day i mod D).  Actions: pre-generated
+    torch.rand((N,1), CPU generator seed 1234)*2-1."""
+
+    def __init__(self, W: int = 60):
+        import datetime
+        import tempfile
+
+        import torch
+        from baseline import reference as ref
+
+        ref.import_reference()
+        from finenvs.environments.time_series_env import TimeSeriesEnv as RefEnv
+
+        self.torch = torch
+        self.W = W
+        prices, _, _, _ = make_series("c2", W)
+        T, bars, _ = WORKLOAD_SERIES["c2"]
+        self._tmp = tempfile.mkdtemp(prefix="fe_refbench_", suffix="_data")   # the path must contain "data" (:47-51)
+        day0 = datetime.date(1998, 1, 2)
+        t0 = time.perf_counter()
+        with open(os.path.join(self._tmp, "dummy.csv"), "w") as f:
+            lines = []
+            for d in range(T // bars):
+                date = (day0 + datetime.timedelta(days=d)).strftime("%m/%d/%Y")
+                for j in range(bars):
+                    o, h, l, c = prices[d * bars + j]
+                    lines.append(f"{date},{9 + (30 + j) // 60:02d}:{(30 + j) % 60:02d},{o:.4f},{h:.4f},{l:.4f},{c:.4f},0\n")
+            f.writelines(lines)
+        torch.manual_seed(ACTION_SEED)
+        self.env = RefEnv(self._tmp, "dummy", num_intervals=W, device_id=-1)
+        self.construct_s = time.perf_counter() - t0
+        self.native_envs = int(self.env.num_envs)
+        self.D = self.native_envs - 1
+
+    def close(self):
+        import shutil
+
+        shutil.rmtree(self._tmp, ignore_errors=True)
+
+    def widen(self, N: int):
+        torch, e = self.torch, self.env
+        e.env_indices = torch.arange(N, dtype=torch.int64) % self.D
+        e.num_envs = N
+        e.env_pointers = torch.zeros((N,), dtype=torch.int64)
+        e.env_spots = torch.arange(0, e.num_intervals).repeat(N, 1)
+        e.cash = e.starting_balance * torch.ones((N, 1))
+        e.long_shares = torch.zeros((N, 1))
+        e.short_shares = torch.zeros((N, 1))
+        e.margin = torch.zeros((N, 1))
+        if hasattr(e, "current_close_prices"):   # :426 reset() keys "no step yet" on this attribute
+            del e.current_close_prices
+
+    def run(self, N: int, threads: int, steps: int, warmup: int, budget_s: float | None):
+        """(env-steps/s, seconds per step, steps timed) of TimeSeriesEnv.step at N envs with `threads` torch threads."""
+        torch = self.torch
+        torch.set_num_threads(threads)
+        self.widen(N)
+        g = torch.Generator().manual_seed(ACTION_SEED)
+        acts = [torch.rand((N, 1), generator=g) * 2 - 1 for _ in range(4)]
+        self.env.reset()
+        for i in range(warmup):
+            self.env.step(acts[i % 4])
+        t0 = time.perf_counter()
+        n = 0
+        for i in range(steps):
+            self.env.step(acts[i % 4])
+            n += 1
+            if budget_s is not None and time.perf_counter() - t0 > budget_s and n >= 3:
+                break
+        dt = time.perf_counter() - t0
+        return N * n / dt, dt / n, n
+
+
+def reference_baseline(W: int, steps: int, warmup: int, budget_each_s: float, with_single_thread: bool, port_workload: str,
+                       widened_envs: int = 65536):
+    """All CPU numbers of one run: the real reference at C1 (N=1024) and widened N=65 536, and the C port."""
+    import torch
+    from baseline import reference as ref
+
+    ncpu = host_threads()
+    out = {"cores": ncpu, "cpu_count": os.cpu_count(), "cpu_model": cpu_model(), "torch": torch.__version__, "runs": []}
+    best = None
+    if ref.available():
+        rr = ReferenceRunner(W)
+        out["reference_constructor_s"] = rr.construct_s
+        sizes = [rr.native_envs] + ([widened_envs] if widened_envs > rr.native_envs else [])
+        plan = [(n, ncpu) for n in sizes] + ([(n, 1) for n in sizes] if with_single_thread else [])
+        for N, th in plan:
+            wu = warmup if N <= 4096 else 1
+            v, sps, n = rr.run(N, th, steps if N <= 4096 else max(3, min(steps, 8)), wu, budget_each_s)
+            run = {"impl": "reference TimeSeriesEnv.step (torch eager, device_id=-1)", "envs": N, "threads": th, "value": v,
+                   "ms_per_step": sps * 1e3, "steps": n}
+            out["runs"].append(run)
+            if th == ncpu and (best is None or v > best["value"]):
+                best = run
+        rr.close()
+    sample = min(WORKLOAD_DEFAULTS[port_workload][0], 262144 // WORKLOAD_ASSETS[port_workload] // (2 if port_workload == "c3" else 1))
+    pv, psps, pth, pn = cpu_port_throughput(WORKLOAD_DEFAULTS[port_workload][1], port_workload, sample, 10_000, 3, min(budget_each_s, 8.0))
+    out["cpu_port"] = {"value": pv, "unit": UNIT, "cores": pth, "kind": "port", "ms_per_step": psps * 1e3,
+                       "sample": f"{sample} envs per step, {pn} steps, oracle/fe_oracle.c (OpenMP, {pth} threads), workload {port_workload}"}
+    out["best"] = best
+    return out
+
+
+def cpu_baseline_block(rb: dict) -> dict:
+    best = rb["best"]
+    if best is None:   # no reference tree on this box: the port is all there is
+        p = rb["cpu_port"]
+        return {**p, "note": "baseline/_ref absent: oracle port only"}
+    return {"value": best["value"], "unit": UNIT, "cores": best["threads"], "kind": "reference", "tree": "baseline/_ref",
+            "sample": (f"unmodified reference TimeSeriesEnv.step, c2 series as CSV, W=60, {best['envs']} envs per step "
+                       f"({'C1 native' if best['envs'] <= 4096 else 'widened, SURVEY App. C.4'}), {best['steps']} steps, "
+                       f"torch.set_num_threads({best['threads']}); best of the all-thread runs"),
+            "ms_per_step": best["ms_per_step"], "cpu_count": rb["cpu_count"], "cpu_model": rb["cpu_model"], "torch": rb["torch"],
+            "runs": rb["runs"], "cpu_port": rb["cpu_port"],
+            "not_timed": "the 1 Mi-env reference step (4 transient ~10 GB copies per step) is not timed"}
+
+
 def run_reference_arm(args, rank: int):
-    """--impl reference: the reference's algorithm on the box's host cores (oracle port, all threads)."""
+    """--impl reference: the reference's own CPU implementation on the box's host cores."""
     if rank != 0:
         return
-    sample = min(args.envs, 262144 // WORKLOAD_ASSETS[args.workload] // (2 if args.workload == "c3" else 1))
-    v, sps, threads, n = cpu_oracle_throughput(args.window, args.workload, sample, args.steps, args.warmup, None)
+    force_host_threads()
+    rb = reference_baseline(60, args.steps, args.warmup, 45.0, True, args.workload, args.ref_widened_envs)
+    cb = cpu_baseline_block(rb)
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
-        "warmup": args.warmup, "ms_per_step": sps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
-        "config": workload_config(args, 1),
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{sample} envs per step, {n} steps, oracle/fe_oracle.c (OpenMP, {threads} threads)"},
-        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": workload_config(args.workload, args.envs, args.window, args.gpus),
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, world: int):
-    return {"workload": WORKLOAD_NAMES[args.workload], "envs_per_gpu": args.envs, "total_envs": args.envs * world,
-            "window": args.window, "assets": WORKLOAD_ASSETS[args.workload], "obs_dtype": "float32", "reset": "all envs redraw (segment, offset), Philox",
-            "parallelism": f"env-sharded x{world}, series replicated, no per-step collective",
-            "l2": "per-step working set (obs >= 1.2 GB + state) >> 126 MB L2: no flush needed"}
-
-
 # ------------------------------------------------------------------------------ GPU arm ------
+class Timer:
+    """K-step blocks timed with CUDA events, barrier + synchronize around every block, max over ranks per block."""
+
+    def __init__(self, torch, dist, dev, world):
+        self.torch, self.dist, self.dev, self.world = torch, dist, dev, world
+
+    def sync_all(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+
+    def blocks(self, fn, steps: int, warmup: int, nblocks: int, wall: bool = False):
+        torch = self.torch
+        stream = torch.cuda.current_stream()
+        k = 0
+        for _ in range(warmup):
+            fn(k)
+            k += 1
+        ms = []
+        for _ in range(nblocks):
+            self.sync_all()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record(stream)
+            for _ in range(steps):
+                fn(k)
+                k += 1
+            e1.record(stream)
+            self.sync_all()
+            t = e0.elapsed_time(e1)
+            if wall:   # a host-synchronous call: the wall clock is the larger of the two
+                t = max(t, (time.perf_counter() - t0) * 1e3)
+            ms.append(t)
+        v = torch.tensor(ms, dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(v, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in v.tolist()]
+
+
+def summarize(ms_blocks, steps: int, total_envs: int):
+    med, lo, hi = float(np.median(ms_blocks)), float(min(ms_blocks)), float(max(ms_blocks))
+    return {"value": total_envs * steps / (med * 1e-3), "ms_per_step": med / steps,
+            "timing": {"blocks": len(ms_blocks), "steps_per_block": steps, "ms_per_step_median": med / steps,
+                       "ms_per_step_min": lo / steps, "ms_per_step_max": hi / steps}}
+
+
+def load_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def roofline_block(workload: str, W: int, N: int, A: int, kernel_s: float, table_bytes: int, kernel_name: str):
+    peak, peak_src = load_peak()
+    alg = algorithmic_bytes_per_env_step(W, A)
+    resident = table_bytes <= L2_RESIDENT_BYTES
+    dram_alg = alg - (window_read_bytes(W, A) if resident else 0)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(f"{workload}_w{W}_n{N}")
+    except Exception:
+        pass
+    achieved = dram_alg * N / kernel_s / 1e9
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "peak_source": f"of {peak_src}",
+            "bytes_per_env_step_counted": dram_alg,
+            "note": ("log-return table is L2-resident: the window reads (W*16*A B per env-step) never reach DRAM and are NOT "
+                     "counted in achieved/frac; algorithmic_* counts them" if resident else
+                     "log-return table >> L2: all algorithmic bytes cross DRAM"),
+            "algorithmic_bytes_per_env_step": alg, "algorithmic_achieved": alg * N / kernel_s / 1e9,
+            "algorithmic_frac": alg * N / kernel_s / 1e9 / peak,
+            "kernel": kernel_name, "kernel_ms": kernel_s * 1e3,
+            "dram_gbs": (traffic / kernel_s / 1e9) if traffic else None,
+            "dram_frac": (traffic / kernel_s / 1e9 / peak) if traffic else None}
+
+
+def measure_workload(torch, par, loader, timer, workload, N, W, rank, world, local_rank, steps, warmup, nblocks, variant,
+                     full: bool):
+    """One workload on this rank's GPU.  full=True adds the public step() and the host-buffer (e2e) legs."""
+    dev = f"cuda:{local_rank}"
+    A = WORKLOAD_ASSETS[workload]
+    total = N * world
+    prices, seg_start, seg_len, meta = make_series(workload, W)
+    series = loader.stage_series(prices, seg_start, seg_len, W, dev, torch.float32)
+    del prices
+    env = par.make_sharded_env(total, rank, world, "bench", num_intervals=W, device_id=local_rank, series=series,
+                               seed=ACTION_SEED, random_reset="all", random_offset=True, variant=variant)
+    assert env.num_envs == N
+    g = torch.Generator(device=dev).manual_seed(ACTION_SEED + rank)
+    ring = [torch.rand((N, A), generator=g, device=dev) * 2 - 1 for _ in range(8)]   # inputs resident in HBM
+    obs = torch.empty((N, W, 5 * A), dtype=torch.float32, device=dev)
+    rewards = torch.empty(N, dtype=torch.float32, device=dev)
+    dones = torch.empty(N, dtype=torch.int32, device=dev)
+
+    out = {}
+    dev_blocks = timer.blocks(lambda i: env.step_into(ring[i % 8], obs, rewards, dones), steps, warmup, nblocks)
+    res = summarize(dev_blocks, steps, total)
+    kernel_s = res["ms_per_step"] * 1e-3   # only fe_step launches sit between the events
+    table_bytes = int(series.logret.numel() * series.logret.element_size())
+    res["roofline"] = roofline_block(workload, W, N, A, kernel_s, table_bytes, env.kernel_name())
+    res["episodes_finished_last_step"] = int(dones.sum().item())
+    launches_per_step = 2 if " + " in env.kernel_name() else 1
+    launches = launches_per_step * steps * nblocks
+    out.update(res)
+    if full:
+        del obs
+        held = []
+
+        def public_step(i):
+            held.clear()
+            held.append(env.step(ring[i % 8]))   # fresh obs / rewards / dones every call, like the reference
+
+        pub = summarize(timer.blocks(public_step, steps, warmup, nblocks), steps, total)
+        held.clear()
+        out["public_step"] = {"value": pub["value"], "unit": UNIT, "ms_per_step": pub["ms_per_step"], "timing": pub["timing"],
+                              "api": "TimeSeriesEnv.step(actions) -> (obs, rewards, dones, info): allocates its outputs"}
+        launches += launches_per_step * steps * nblocks
+        ring_host = [a.cpu().pin_memory() for a in ring[:4]]
+        check = [0.0]
+
+        def host_step(i):
+            _, r_h, d_h, _ = env.step_host(ring_host[i % 4])
+            check[0] += float(r_h[0]) + int(d_h[0])   # the host reads the step's result
+
+        e2e = summarize(timer.blocks(host_step, steps, warmup, nblocks, wall=True), steps, total)
+        h2d, d2h = env.host_bytes_per_step()
+        out["e2e"] = {"value": e2e["value"], "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                      "ms_per_step": e2e["ms_per_step"], "timing": e2e["timing"],
+                      "api": "TimeSeriesEnv.step_host -> fe_step_host (pinned host buffers)"}
+        launches += launches_per_step * steps * nblocks
+    out["gpu_launches"] = launches
+    out["meta"] = meta
+    del env, series, ring
+    torch.cuda.empty_cache()
+    return out
+
+
+def measure_collectives(torch, dist, par, dev, world, N):
+    """Device time (CUDA events, max over ranks) of the collectives the path uses outside the step."""
+    def timed(fn, reps=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps * 1e3], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    stats = torch.zeros(5, dtype=torch.float64, device=dev)
+    fit = torch.rand(N, device=dev)
+    out = {"world": world, "unit": "us", "backend": dist.get_backend()}
+    out["episode_stats_all_reduce_5xf64"] = timed(lambda: dist.all_reduce(stats, op=dist.ReduceOp.SUM))
+    out[f"es_fitness_all_gather_{N}xf32_per_rank"] = timed(lambda: par.all_gather_fitness(fit, N * world))
+    for name, n in (("300-8-1", 2417), ("300-256-256-1", 143105)):
+        grad = torch.zeros(n, device=dev)
+        out[f"es_gradient_all_reduce_{name}_{n}xf32"] = timed(lambda: dist.all_reduce(grad, op=dist.ReduceOp.SUM))
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -212,14 +547,18 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"])
     ap.add_argument("--envs", type=int, default=None, help="envs per GPU (default: 1 Mi; c3: 65536)")
     ap.add_argument("--window", type=int, default=None, help="default 60; c3: 128")
-    ap.add_argument("--variant", default="auto", choices=["auto", "tile", "direct", "pipe", "scatter", "split", "rows"])
+    ap.add_argument("--variant", default="auto")
+    ap.add_argument("--blocks", type=int, default=None, help="how many times the K-step block is timed (default: ~200 steps in total, 3..10)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-widened-envs", type=int, default=65536,
+                    help="second size the unmodified reference is timed at (SURVEY App. C.4 widening); 0 = native N=1024 only")
+    ap.add_argument("--no-also", action="store_true", help="skip the other workloads / collectives")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to its GPU's NUMA-local CPUs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     args.envs = args.envs or WORKLOAD_DEFAULTS[args.workload][0]
     args.window = args.window or WORKLOAD_DEFAULTS[args.workload][1]
-    A = WORKLOAD_ASSETS[args.workload]
+    nblocks = args.blocks or max(3, min(10, -(-200 // args.steps)))
 
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":
@@ -238,83 +577,26 @@ def main():
     rank, world, local_rank = par.init_distributed("nccl")
     torch.cuda.set_device(local_rank)
     dev = f"cuda:{local_rank}"
-    W, N = args.window, args.envs
-    total = N * world
+    timer = Timer(torch, dist, dev, world)
 
-    prices, seg_start, seg_len, meta = make_series(args.workload, W)
-    series = loader.stage_series(prices, seg_start, seg_len, W, dev, torch.float32)
-    env = par.make_sharded_env(total, rank, world, "bench", num_intervals=W, device_id=local_rank, series=series,
-                               seed=ACTION_SEED, random_reset="all", random_offset=True, variant=args.variant)
-    assert env.num_envs == N
-
-    # inputs resident in HBM: a ring of pre-generated action batches
-    g = torch.Generator(device=dev).manual_seed(ACTION_SEED + rank)
-    ring = [torch.rand((N, A), generator=g, device=dev) * 2 - 1 for _ in range(8)]
-    obs = torch.empty((N, W, 5 * A), dtype=torch.float32, device=dev)
-    rewards = torch.empty(N, dtype=torch.float32, device=dev)
-    dones = torch.empty(N, dtype=torch.int32, device=dev)
-    ring_host = [a.cpu().pin_memory() for a in ring[:4]]
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-
-    def max_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    stream = torch.cuda.current_stream()
     sampler = ClockSampler(local_rank)
     with sampler:
-        # ---- device-resident: `value` and the kernel's roofline --------------------------------
-        for i in range(args.warmup):
-            env.step_into(ring[i % 8], obs, rewards, dones)
-        sync_all()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for i in range(args.steps):
-            env.step_into(ring[i % 8], obs, rewards, dones)
-        e1.record(stream)
-        sync_all()
-        dev_ms = max_over_ranks(e0.elapsed_time(e1))
-        n_done = int(dones.sum().item())
-
-        # ---- end to end through the host-buffer C-ABI call ----------------------------------------
-        for i in range(args.warmup):
-            env.step_host(ring_host[i % 4])
-        sync_all()
-        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t_wall = time.perf_counter()
-        e2.record(stream)
-        checksum = 0.0
-        for i in range(args.steps):
-            _, r_h, d_h, _ = env.step_host(ring_host[i % 4])
-            checksum += float(r_h[0]) + int(d_h[0])   # the host reads the step's result
-        e3.record(stream)
-        sync_all()
-        e2e_ms = max_over_ranks(max(e2.elapsed_time(e3), (time.perf_counter() - t_wall) * 1e3))
-
-    value = total * args.steps / (dev_ms * 1e-3)
-    e2e_value = total * args.steps / (e2e_ms * 1e-3)
-    bytes_per_launch = algorithmic_bytes_per_env_step(W, A) * N
-    kernel_s = dev_ms * 1e-3 / args.steps   # only fe_step launches sit between the two events
-    achieved = bytes_per_launch / kernel_s / 1e9
-    peak, peak_src = 6650.0, "fallback"
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured"
-    except Exception:
-        pass
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(f"{args.workload}_w{W}_n{N}")
-    except Exception:
-        pass
+        main_res = measure_workload(torch, par, loader, timer, args.workload, args.envs, args.window, rank, world, local_rank,
+                                    args.steps, args.warmup, nblocks, args.variant, full=True)
+    also, collectives = {}, None
+    if not args.no_also:
+        others = [w for w in (("c4", "c3") if world == 1 else ("c4",)) if w != args.workload]
+        for w in others:
+            n, win = WORKLOAD_DEFAULTS[w]
+            r = measure_workload(torch, par, loader, timer, w, n, win, rank, world, local_rank, args.steps, args.warmup,
+                                 nblocks, "auto", full=False)
+            also[w] = {"workload": WORKLOAD_NAMES[w], "envs_per_gpu": n, "window": win, "assets": WORKLOAD_ASSETS[w],
+                       "value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"], "timing": r["timing"],
+                       "kernel": r["roofline"]["kernel"], "frac": r["roofline"]["frac"], "dram_frac": r["roofline"]["dram_frac"],
+                       "algorithmic_frac": r["roofline"]["algorithmic_frac"], "roofline": r["roofline"],
+                       "gpu_launches": r["gpu_launches"]}
+        if world > 1:
+            collectives = measure_collectives(torch, dist, par, dev, world, args.envs)
 
     if rank != 0:
         if world > 1:
@@ -323,34 +605,30 @@ def main():
         return
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32/f64", "data": "synthetic", "config": {**workload_config(args, world), **meta},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": f"of {peak_src}",
-                     "algorithmic_bytes_per_env_step": algorithmic_bytes_per_env_step(W, A),
-                     "kernel": env.kernel_name(),
-                     "kernel_ms": kernel_s * 1e3,
-                     # what DRAM actually carried (ncu) over the same launch time: when the series is L2-resident the
-                     # window reads never reach DRAM, so `frac` (algorithmic bytes) can exceed 1 while this stays below
-                     "dram_gbs": (traffic / kernel_s / 1e9) if traffic else None,
-                     "dram_frac": (traffic / kernel_s / 1e9 / peak) if traffic else None},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * N * A, "d2h_bytes_per_step": 8 * N,
-                "ms_per_step": e2e_ms / args.steps, "api": "TimeSeriesEnv.step_host -> fe_step_host (pinned host buffers)"},
-        # kernels of this library inside the two timed regions (device + e2e legs): one per step, two where the step is
-        # a bookkeeping + a streaming launch (portfolio, split); with pinned buffers the host step is the same launch(es)
-        "gpu_launches": 2 * args.steps * (2 if " + " in env.kernel_name() else 1),
+        "metric": METRIC, "value": main_res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32/f64", "data": "synthetic", "config": workload_config(args.workload, args.envs, args.window, world),
+        "timing": main_res["timing"],
+        "roofline": main_res["roofline"],
+        "e2e": main_res["e2e"],
+        "public_step": main_res["public_step"],
+        # kernels of this library inside the timed regions (device, public step() and e2e legs; + the `also` workloads):
+        # one per step, two where the step is a bookkeeping + a streaming launch (portfolio, split)
+        "gpu_launches": main_res["gpu_launches"] + sum(a["gpu_launches"] for a in also.values()),
         "clocks": sampler.summary(),
-        "episodes_finished_last_step": n_done,
+        "episodes_finished_last_step": main_res["episodes_finished_last_step"],
     }
-    line["config"]["numa_bound_cpus"] = len(os.sched_getaffinity(0)) if prev_affinity is not None else None
+    if also:
+        line["also"] = also
+    if collectives:
+        line["collectives"] = collectives
+    line["host"] = {"numa_bound_cpus": len(os.sched_getaffinity(0)) if prev_affinity is not None else None,
+                    "cpu_count": os.cpu_count()}
     if prev_affinity is not None:
         os.sched_setaffinity(0, prev_affinity)   # the CPU baseline uses every host core
     if world == 1 and not args.no_cpu_baseline:
-        sample = min(N, 262144 // A // (2 if A > 1 else 1))
-        v, sps, threads, n = cpu_oracle_throughput(W, args.workload, sample, 10_000, 3, 12.0)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"{sample} envs per step, {n} steps (~12 s), oracle/fe_oracle.c, OpenMP {threads} threads"}
+        rb = reference_baseline(60, 30, 3, 10.0, False, args.workload, args.ref_widened_envs)
+        line["cpu_baseline"] = cpu_baseline_block(rb)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -462,6 +462,11 @@ class TimeSeriesEnv(BaseObject):
         info_dict = self.record_evaluation_metrics() if self.evaluate else {}
         return (obs, rewards, dones, info_dict)
 
+    def host_bytes_per_step(self) -> Tuple[int, int]:
+        """(host->device, device->host) bytes one step_host() call moves over PCIe."""
+        osz = 8 if self.obs_dtype == torch.float64 else 4
+        return 4 * self.num_envs * self.num_acts, (osz + 4) * self.num_envs
+
     # ------------------------------------------------------------------ captured rollouts (8f-4) ----
     def _observe_into(self, obs: torch.Tensor) -> None:
         _lib.check(self._L.fe_observe(self._pp, self._ps, self._pst, obs.data_ptr(), self._stream()), "fe_observe")
