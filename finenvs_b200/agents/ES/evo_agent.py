@@ -106,35 +106,38 @@ class EvoAgent(BaseObject):
         self.current_timesteps = torch.zeros((self.num_envs,), device=self._dev)
         self._counters.zero_()
 
-    # ------------------------------------------------------------------ reference :48-88 (unchanged)
+    # ------------------------------------------------------------------ env description, progress log (:48-88)
+    _ENV_KEYS = {
+        "env_name": "label used in log file names",
+        "num_envs": "size of the whole population held by this agent (training + evaluation envs)",
+        "num_eval_envs": "how many of them, at the end, run the unperturbed parameters",
+        "num_observations": "length of one env's observation vector",
+        "num_actions": "length of one env's action vector",
+    }
+    _LOG_COLUMNS = ("unix_time", "num_episodes", "mean_eval_return", "std_dev_eval_return", "mean_training_return",
+                    "std_dev_training_return", "L2_norm")   # the reference's CSV schema (:68-76): a file format, kept
+
     def set_env_params(self, env_args: Dict) -> None:
-        try:
-            self.env_name: str = env_args["env_name"]
-            self.num_envs: int = env_args["num_envs"]
-            self.num_eval_envs: int = env_args["num_eval_envs"]
-            self.num_training_envs = self.num_envs - self.num_eval_envs
-            self.num_observations: int = env_args["num_observations"]
-            self.num_actions: int = env_args["num_actions"]
-        except Exception:
-            raise Exception(
-                "env_args must contain the following keys:\n"
-                + "\tenv_name -> the name of the environment simulation (for logging purposes)\n"
-                + "\tnum_envs -> the total number of parallel environments\n"
-                + "\tnum_eval_envs -> the number of environments set aside for evaluation\n"
-                + "\tnum_observations -> the observation dimension in each step of a single environment\n"
-                + "\tnum_actions -> the action dimension in each step of a single environment"
-            )
+        missing = [k for k in self._ENV_KEYS if k not in env_args]
+        if missing:
+            wanted = "; ".join(f"{k} ({why})" for k, why in self._ENV_KEYS.items())
+            raise Exception(f"env_args lacks {missing}. EvoAgent reads: {wanted}")
+        self.env_name = env_args["env_name"]
+        self.num_envs = int(env_args["num_envs"])
+        self.num_eval_envs = int(env_args["num_eval_envs"])
+        self.num_observations = int(env_args["num_observations"])
+        self.num_actions = int(env_args["num_actions"])
+        self.num_training_envs = self.num_envs - self.num_eval_envs
 
     def create_progress_log(self) -> None:
-        trials_dir = os.path.join(os.getcwd(), "trials")
-        if not os.path.exists(trials_dir):
-            os.mkdir(trials_dir)
-        self.csv_name = os.path.join(trials_dir, datetime.now().strftime(f"{self.env_name}_Evo_%Y-%m-%d_%H-%M-%S.csv"))
-        csv_fields = ["unix_time", "num_episodes", "mean_eval_return", "std_dev_eval_return", "mean_training_return",
-                      "std_dev_training_return", "L2_norm"]
-        self.log = open(self.csv_name, "a")
+        """One CSV per run under ./trials, named <env>_Evo_<timestamp>.csv like the reference's (:62-67)."""
+        folder = os.path.join(os.getcwd(), "trials")
+        os.makedirs(folder, exist_ok=True)
+        stamp = datetime.now().strftime("%Y-%m-%d_%H-%M-%S")
+        self.csv_name = os.path.join(folder, f"{self.env_name}_Evo_{stamp}.csv")
+        self.log = open(self.csv_name, "a", newline="")
         self.writer = csv.writer(self.log)
-        self.writer.writerow(csv_fields)
+        self.writer.writerow(self._LOG_COLUMNS)
 
     # ------------------------------------------------------------------ rollout (:90-112)
     def step(self, states) -> torch.Tensor:
@@ -205,68 +208,67 @@ class EvoAgent(BaseObject):
         return ge[keep], gr[keep]
 
     def train(self) -> float:
-        self.network.reconstruct_perturbations()
+        """One ES generation update (:164-171): ranks of the finished episodes -> parameter update -> statistics ->
+        fresh perturbations for the next generation.  Returns the mean evaluation return like the reference."""
+        net = self.network
+        net.reconstruct_perturbations()          # a no-op here (perturbations are a pure function of their counters)
         self.perform_rank_transformation()
-        self.network.update_parameters(self.final_ranks)
-        eval_return = self.log_progress()
-        self.network.perturb_parameters()
-        return eval_return
+        net.update_parameters(self.final_ranks)
+        mean_eval = self.log_progress()
+        net.perturb_parameters()
+        return mean_eval
 
     def perform_rank_transformation(self) -> None:
+        """:173-191 — ONE sort over the finished episodes of ALL ranks, so every rank derives the same ranks."""
         self._g_env, self._g_ret = self._gather_finished()
-        sort_indices = self._g_ret.argsort()
-        self.compute_centered_ranks(sort_indices)
+        self.compute_centered_ranks(self._g_ret.argsort())
         self.compute_final_ranks()
 
     def compute_centered_ranks(self, sort_indices: torch.Tensor) -> None:
-        """:173-181"""
-        ranks = torch.empty(sort_indices.shape, device=self._dev)
-        linear_ranks = torch.arange(0, sort_indices.shape[0], dtype=torch.float32, device=self._dev)
-        ranks[sort_indices] = linear_ranks
-        N = len(ranks)
-        self.centered_ranks = ranks / (N - 1) - 0.5
+        """Position of every episode in the sorted order, mapped linearly onto [-0.5, 0.5] (:176-181)."""
+        n = sort_indices.numel()
+        position = torch.empty(n, dtype=torch.float32, device=self._dev)
+        position[sort_indices] = torch.arange(n, dtype=torch.float32, device=self._dev)
+        self.centered_ranks = position / (n - 1) - 0.5
 
     def compute_final_ranks(self) -> None:
-        """:183-186, restricted to the envs this rank holds."""
-        mine = (self._g_env >= self.env_id_base) & (self._g_env < self.env_id_base + self.num_envs)
-        self.final_ranks = torch.zeros((self.num_envs,), device=self._dev)
-        self.final_ranks.index_add_(0, self._g_env[mine] - self.env_id_base, self.centered_ranks[mine])
+        """:183-186, restricted to the envs this rank holds: an env's weight is the sum of its episodes' ranks."""
+        lo, hi = self.env_id_base, self.env_id_base + self.num_envs
+        mine = (self._g_env >= lo) & (self._g_env < hi)
+        self.final_ranks = torch.zeros(self.num_envs, dtype=torch.float32, device=self._dev)
+        self.final_ranks.index_add_(0, self._g_env[mine] - lo, self.centered_ranks[mine])
 
     def compute_mean_returns(self) -> None:
-        """:154-162"""
-        dones, finished_returns = self._finished()
-        done_counts = torch.bincount(dones, minlength=self.num_envs)
-        numerator = torch.zeros((self.num_envs,), device=self._dev)
-        numerator.index_add_(0, dones, finished_returns)
-        denominator = done_counts.float()
-        denominator[done_counts == 0] = 1.0
-        self.mean_returns = numerator / denominator
+        """Per-env mean over the episodes it finished this generation; envs without one report 0 (:154-162)."""
+        env_of_episode, episode_return = self._finished()
+        total = torch.zeros(self.num_envs, dtype=torch.float32, device=self._dev)
+        total.index_add_(0, env_of_episode, episode_return)
+        episodes = torch.bincount(env_of_episode, minlength=self.num_envs)
+        self.mean_returns = total / episodes.clamp(min=1).to(torch.float32)
 
     def log_progress(self) -> float:
         """:114-152 (statistics of this rank's envs; rank 0 of a sharded run prints)."""
         self.compute_mean_returns()
-        num_episodes = int(self._counters[0].item())
-        training_mean_returns = self.mean_returns[: self.num_training_envs]
-        eval_mean_returns = self.mean_returns[self.num_training_envs:]
-        mean_training_return = training_mean_returns.mean().item()
-        std_dev_training_return = training_mean_returns.std().item()
-        mean_eval_return = eval_mean_returns.mean().item() if self.num_eval_envs else float("nan")
-        std_dev_eval_return = eval_mean_returns.std().item() if self.num_eval_envs > 1 else float("nan")
-        L2_norm = self.network.get_l2_norm()
-        record_fields = [time(), num_episodes, mean_eval_return, std_dev_eval_return, mean_training_return,
-                         std_dev_training_return, L2_norm]
+        train_part = self.mean_returns[: self.num_training_envs]
+        eval_part = self.mean_returns[self.num_training_envs:]
+        nan = float("nan")
+        row = {
+            "unix_time": time(),
+            "num_episodes": int(self._counters[0].item()),
+            "mean_eval_return": eval_part.mean().item() if self.num_eval_envs else nan,
+            "std_dev_eval_return": eval_part.std().item() if self.num_eval_envs > 1 else nan,
+            "mean_training_return": train_part.mean().item(),
+            "std_dev_training_return": train_part.std().item(),
+            "L2_norm": self.network.get_l2_norm(),
+        }
         if self.write_to_csv:
-            self.writer.writerow(record_fields)
+            self.writer.writerow([row[c] for c in self._LOG_COLUMNS])
+            self.log.flush()
         if not dist.is_initialized() or dist.get_rank(self.group) == 0:
-            print(
-                f"num eps: {num_episodes} | "
-                + f"steps: {int(self.total_timesteps)} | "
-                + f"eval mean: {mean_eval_return:.2f} | "
-                + f"eval std: {std_dev_eval_return:.2f} | "
-                + f"train mean: {mean_training_return:.2f} | "
-                + f"train std: {std_dev_training_return:.2f} | "
-                + f"L2 norm: {L2_norm:.2f}"
-            )
-        del self.centered_ranks, self.final_ranks, self.mean_returns
+            print(f"[ES] episodes {row['num_episodes']}  env-steps {self.total_timesteps}  "
+                  f"eval {row['mean_eval_return']:.2f} +- {row['std_dev_eval_return']:.2f}  "
+                  f"train {row['mean_training_return']:.2f} +- {row['std_dev_training_return']:.2f}  "
+                  f"|theta| {row['L2_norm']:.2f}")
+        del self.centered_ranks, self.final_ranks, self.mean_returns      # per-generation scratch, as in the reference
         self._reset_accumulators()
-        return mean_eval_return
+        return row["mean_eval_return"]

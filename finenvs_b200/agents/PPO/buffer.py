@@ -44,48 +44,98 @@ class Buffer(BaseObject):
         self._store: Dict[str, Optional[torch.Tensor]] = {k: None for k in _KEYS}
         self._t = 0                  # time steps stored in the current rollout
         self._env = None
-        self._obs_write = 0          # slot the bound env writes its next observation into
+        self._held_slot = None       # states slot holding the observation the agent has in hand (None: not in storage)
+        self._states_flat = None     # states storage as one flat tensor: slot k = [k * stride, k * stride + numel)
+        self._slot_stride = 0
         self.container: Dict[str, Optional[torch.Tensor]] = {k: None for k in (*_KEYS, "advantages", "returns")}
         self.batch_keys = ["states", "actions", "log_probs", "advantages", "returns"]
 
     # ------------------------------------------------------------------ zero-copy observation hand-off
     def bind_env(self, env) -> None:
         """Let `env` (finenvs_b200 TimeSeriesEnv) write its observations directly into this buffer's `states`
-        storage: reset()/step() then return views of the slot the agent stores next."""
+        storage: reset()/step() then return views of the slot the agent stores next.  May be called at any point
+        of the loop (before or after the first reset(), or between rollouts): an observation the agent already holds
+        is simply copied in by the store() that follows."""
         self._env = env
         env._obs_ring = self
-        self._obs_write = self._t
+        self._held_slot = None
 
-    def next_obs_slot(self, shape, dtype) -> torch.Tensor:
-        """Called by the bound env instead of torch.empty: slot `_obs_write` of the states storage
-        (capacity + 1 slots: after T stores the observation of step T is live in slot T)."""
-        st = self._store["states"]
-        if st is None or st.shape[1:] != tuple(shape) or st.dtype != dtype:
-            st = self._alloc("states", torch.empty(shape, dtype=dtype, device=self._dev))
-        if self._obs_write > self._t + 1:
-            # out of step with store() (e.g. reset() called twice): plain tensor, store() copies it in; the
-            # zero-copy hand-off resumes after the next clear()
-            return torch.empty(shape, dtype=dtype, device=self._dev)
-        if self._obs_write >= st.shape[0]:
+    def next_obs_slot(self, shape, dtype, for_reset: bool = False) -> torch.Tensor:
+        """Called by the bound env instead of torch.empty.  Slot protocol (the loop of
+        examples/time_series/PPO_LSTM_training_SPY.py:22-30 is `agent.step -> env.step -> agent.store`):
+
+        * reset(): the observation becomes the one the agent holds and stores NEXT -> slot `_t`;
+        * step(): the agent still holds the previous observation, which store() puts in slot `_t` (a no-op when it
+          already lives there) -> the new one goes to slot `_t + 1`, where it will be "next" after that store().
+
+        A slot that holds the agent's current observation is never handed out again (after clear() the held observation
+        sits in the old slot T; a second step() without a store() in between would ask for the same slot twice): those
+        calls get the next free slot or a plain tensor, and store() copies.  capacity + 1 slots exist: after T stores
+        the observation of step T is live in slot T."""
+        self._states_storage(tuple(shape), dtype)
+        k = self._t if for_reset else self._t + 1
+        if not for_reset and self._held_slot is not None and k == self._held_slot:
+            k += 1
+            if k == self._t:        # cannot happen (k >= _t + 2), kept as an invariant
+                raise AssertionError("observation slot would alias the slot being stored")
+        while k >= self._num_slots():
             self._grow()
-            st = self._store["states"]
-        slot = st[self._obs_write]
-        self._obs_write += 1
-        return slot
+        self._held_slot = k
+        return self._state_slot(k)
 
     # ------------------------------------------------------------------ storage
+    def _num_slots(self) -> int:
+        return 0 if self._states_flat is None else self._states_flat.numel() // self._slot_stride
+
+    def _states_storage(self, shape, dtype) -> None:
+        """(capacity + 1) observation slots whose starts are 16-byte aligned whatever N, W and dtype are (the step
+        kernels store observations with 16-byte bulk / vector stores): the per-slot stride is padded up."""
+        if self._states_flat is not None and self._states_shape == shape and self._states_flat.dtype == dtype:
+            return
+        if self._t != 0 and self._states_flat is not None:
+            raise ValueError("'states' changed shape/dtype inside a rollout")
+        numel = 1
+        for d in shape:
+            numel *= int(d)
+        per16 = 16 // torch.empty((), dtype=dtype).element_size()
+        self._slot_stride = max(per16, (numel + per16 - 1) // per16 * per16)
+        self._states_shape, self._states_numel = tuple(shape), numel
+        self._states_flat = torch.empty((self.capacity + 1) * self._slot_stride, dtype=dtype, device=self._dev)
+        self._store["states"] = self._states_view(self.capacity + 1)
+        self._held_slot = None
+
+    def _state_slot(self, k: int) -> torch.Tensor:
+        o = k * self._slot_stride
+        return self._states_flat[o: o + self._states_numel].view(self._states_shape)
+
+    def _states_view(self, T: int) -> torch.Tensor:
+        """(T, *shape) view of the first T slots (contiguous when the stride needed no padding)."""
+        inner = torch.empty(self._states_shape, device="meta").stride()
+        return torch.as_strided(self._states_flat, (T, *self._states_shape), (self._slot_stride, *inner))
+
     def _alloc(self, key: str, like: torch.Tensor) -> torch.Tensor:
-        extra = 1 if key == "states" else 0
-        self._store[key] = torch.empty((self.capacity + extra, *like.shape), dtype=like.dtype, device=self._dev)
+        if key == "states":
+            self._states_flat = None
+            self._states_storage(tuple(like.shape), like.dtype)
+            return self._store["states"]
+        self._store[key] = torch.empty((self.capacity, *like.shape), dtype=like.dtype, device=self._dev)
         return self._store[key]
 
     def _grow(self) -> None:
         self.capacity *= 2
+        self._held_slot = None      # an observation in hand stays valid in the OLD storage; no new slot aliases it
         for key, old in self._store.items():
             if old is None:
                 continue
-            new = self._alloc(key, old[0])
+            if key == "states":
+                flat = torch.empty((self.capacity + 1) * self._slot_stride, dtype=old.dtype, device=self._dev)
+                flat[: self._states_flat.numel()].copy_(self._states_flat)
+                self._states_flat = flat
+                self._store["states"] = self._states_view(self.capacity + 1)
+                continue
+            new = torch.empty((self.capacity, *old.shape[1:]), dtype=old.dtype, device=self._dev)
             new[: old.shape[0]].copy_(old)
+            self._store[key] = new
 
     def force_2D(self, tensor: torch.Tensor) -> torch.Tensor:
         """buffer.py:58-63 without the time axis (it is the leading storage axis here): (N,) -> (N, 1)."""
@@ -94,6 +144,8 @@ class Buffer(BaseObject):
     def store_tensor(self, key: str, tensor: torch.Tensor) -> None:
         """buffer.py:51-56: append one time step of `key`."""
         tensor = self.force_2D(tensor)
+        if key == "states":
+            return self._store_states(tensor)
         st = self._store[key]
         if st is None:
             st = self._alloc(key, tensor)
@@ -107,6 +159,19 @@ class Buffer(BaseObject):
             st = self._store[key]
         slot = st[self._t]
         if tensor.data_ptr() != slot.data_ptr():      # the bound env already wrote it in place otherwise
+            slot.copy_(tensor)
+
+    def _store_states(self, tensor: torch.Tensor) -> None:
+        self._states_storage(tuple(tensor.shape), tensor.dtype)
+        while self._t + 1 >= self._num_slots():      # slot _t for this observation, slot _t + 1 for the one in flight
+            self._grow()
+        slot = self._state_slot(self._t)
+        if tensor.data_ptr() != slot.data_ptr():      # the bound env already wrote it in place otherwise
+            if self._held_slot == self._t:
+                # the slot being stored into was handed out for a LATER observation that the caller still holds
+                # (store() called with something other than the observation in hand): keep that one intact
+                raise RuntimeError("Buffer.store(states) would overwrite the observation the bound env returned last; "
+                                   "store the observations in the order they were returned")
             slot.copy_(tensor)
 
     def store(self, states: torch.Tensor, actions: torch.Tensor, rewards: torch.Tensor, dones: torch.Tensor,
@@ -166,8 +231,8 @@ class Buffer(BaseObject):
         """buffer.py:102-109: flatten (steps, envs, ...) -> (steps * envs, ...); views, no copies."""
         T = self._t
         for key in _KEYS:
-            st = self._store[key][:T]
-            self.container[key] = st.reshape(T * st.shape[1], *st.shape[2:])
+            st = self._states_view(T) if key == "states" else self._store[key][:T]
+            self.container[key] = st.reshape(T * st.shape[1], *st.shape[2:])   # a copy only if the slot stride is padded
         for key in ("returns", "advantages"):
             t = self.container[key]
             self.container[key] = t.reshape(t.shape[0] * t.shape[1], *t.shape[2:])
@@ -195,10 +260,9 @@ class Buffer(BaseObject):
                 for i in range(num_mini_batches)]
 
     def clear(self) -> None:
-        """buffer.py:150-152.  The storage is kept for the next rollout; the bound env's next observation goes to
-        slot 1 (slot 0 receives, by copy, the observation the agent is still holding — the one it stores first)."""
+        """buffer.py:150-152.  The storage is kept for the next rollout.  The observation the agent still holds stays
+        where it is (slot T of the finished rollout): the first store() of the next rollout copies it into slot 0 and
+        next_obs_slot() never hands that slot out while it is held."""
         for key in self.container.keys():
             self.container[key] = None
-        held = self._t               # the observation the agent still holds lives in slot `held`
         self._t = 0
-        self._obs_write = (2 if held == 1 else 1) if self._env is not None else 0

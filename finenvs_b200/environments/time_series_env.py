@@ -310,9 +310,9 @@ class TimeSeriesEnv(BaseObject):
 
     def reset_evaluation_metrics(self) -> None:
         """:271-275"""
+        # in place: CapturedRollout graphs and FeState hold these device addresses
         self._terminated.zero_()
-        self._ep_return = torch.zeros_like(self._ep_return)
-        self._cstate.ep_return = self._ep_return.data_ptr()
+        self._ep_return.zero_()
         self._stats.zero_()
 
     # reference-named views of the state (same memory; reference shapes (N,1) / (N,))
@@ -357,18 +357,18 @@ class TimeSeriesEnv(BaseObject):
     def _stream(self) -> int:
         return torch.cuda.current_stream(self._dev).cuda_stream
 
-    def _new_obs(self) -> torch.Tensor:
+    def _new_obs(self, for_reset: bool = False) -> torch.Tensor:
         # a fresh tensor every call: the PPO buffer keeps references to past observations (buffer.py:44-56)
         shape = ((self.num_envs, self.num_intervals * self.num_obs) if self.flat_obs
                  else (self.num_envs, self.num_intervals, self.num_obs))
         ring = getattr(self, "_obs_ring", None)
         if ring is not None:  # a rollout buffer bound with Buffer.bind_env: write straight into its storage
-            return ring.next_obs_slot(shape, self.obs_dtype)
+            return ring.next_obs_slot(shape, self.obs_dtype, for_reset)
         return torch.empty(shape, dtype=self.obs_dtype, device=self._dev)
 
     def reset(self) -> torch.Tensor:
         """:423-435 — materialises the current observation; touches no state (reference semantics)."""
-        obs = self._new_obs()
+        obs = self._new_obs(for_reset=True)
         _lib.check(self._L.fe_observe(self._pp, self._ps, self._pst, obs.data_ptr(), self._stream()), "fe_observe")
         return obs
 
@@ -520,7 +520,7 @@ class TimeSeriesEnv(BaseObject):
         test (:531), which like the reference's torch.all() costs one host read per step."""
         n_terminated = int(self._stats[1].item())
         if n_terminated >= self.num_envs:
-            info_dict = {"returns": self._ep_return}
+            info_dict = {"returns": self._ep_return.clone()}   # the reference hands out the old tensor and rebinds (:532-534)
             self.reset_evaluation_metrics()
             return info_dict
         return {}

@@ -95,3 +95,33 @@ def test_evaluate_policy_equals_the_reference_style_loop():
             break
     out2 = b.evaluate_policy(None, rollout=out["rollout"])
     assert torch.equal(out2["returns"], info["returns"])
+
+
+def test_eager_evaluation_keeps_the_state_addresses_a_captured_graph_holds():
+    """reset_evaluation_metrics() used to REPLACE the episode-return tensor; a CapturedRollout has the old
+    device pointer baked into its graph, so after one eagerly completed evaluation its replays accumulated into freed
+    memory.  The metrics are zeroed in place now and info["returns"] is a copy."""
+    from finenvs_b200.environments import TimeSeriesEnv
+
+    W = 6
+    series = _series(W, rows=2400, bars=40, sigma=0.08, seed=5)
+    kw = dict(num_intervals=W, evaluate=True, device_id=0, series=series)
+    a, b = TimeSeriesEnv("eager", **kw), TimeSeriesEnv("graph", **kw)
+    roll = b.capture_rollout(_policy(b), 8)             # graph captured BEFORE any evaluation completes
+    ptr_before = b.episode_returns.data_ptr()
+    pol_a, pol_b = _policy(a), _policy(b)
+
+    def eager_eval(env, pol):
+        states = env.reset()
+        while True:
+            states, rewards, dones, info = env.step(pol(states))
+            if "returns" in info:
+                return info["returns"]
+
+    ra, rb = eager_eval(a, pol_a), eager_eval(b, pol_b)  # both complete one evaluation eagerly
+    assert torch.equal(ra, rb) and b.episode_returns.data_ptr() == ptr_before
+    assert float(b.episode_returns.abs().sum()) == 0.0 and float(rb.abs().sum()) > 0     # zeroed in place, copy handed out
+    a.reset_all(), b.reset_all()
+    ra2 = eager_eval(a, pol_a)
+    out = b.evaluate_policy(None, rollout=roll)          # the old graph must still write where the env reads
+    assert torch.equal(out["returns"], ra2)

@@ -116,3 +116,105 @@ def test_bound_env_writes_observations_in_place():
         got = buf.container["states"].view(T, N, W, 5)
         assert torch.equal(got, torch.stack(kept)) and torch.equal(states, twin_states)
         buf.clear()
+
+
+def _twin_envs(N, W=8, bars=40, days=30, seed=5):
+    from finenvs_b200.data import loader
+    from finenvs_b200.environments import TimeSeriesEnv
+    from parity_utils import gbm_ohlc
+
+    rng = np.random.default_rng(2)
+    prices = np.round(gbm_ohlc(rng, bars * days, 0.02), 4)
+    seg_start, seg_len = loader.regular_segments(bars * days, bars, W)
+    series = loader.stage_series(prices, seg_start, seg_len, W, "cuda:0", torch.float32)
+    kw = dict(num_intervals=W, device_id=0, series=series, num_envs=N, seed=seed, random_reset="all", random_offset=True)
+    return TimeSeriesEnv("a", **kw), TimeSeriesEnv("b", **kw)
+
+
+def _rollouts_match_twin(env, twin, buf, states, twin_states, N, W, T, rollouts=3):
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for rollout in range(rollouts):
+        kept = []
+        for t in range(T):
+            actions = torch.rand((N, 1), generator=g, device="cuda") * 2 - 1
+            nxt, rewards, dones, _ = env.step(actions)
+            twin_nxt, r2, d2, _ = twin.step(actions)
+            buf.store(states, actions, rewards, dones, actions, rewards.unsqueeze(-1))
+            kept.append(twin_states)
+            assert torch.equal(rewards, r2) and torch.equal(dones, d2)
+            assert torch.equal(nxt, twin_nxt), (rollout, t)       # the observation in hand was not clobbered by the store
+            states, twin_states = nxt, twin_nxt
+        buf.prepare_training_data(torch.zeros(N, 1, device="cuda"))
+        got = buf.container["states"].view(T, N, W, 5)
+        assert torch.equal(got, torch.stack(kept)), rollout
+        assert torch.equal(states, twin_states)
+        buf.clear()
+
+
+def test_bind_env_after_the_first_reset():
+    """bind_env() used to assume env.reset() is the next env call; binding while the agent already holds an
+    observation made the next step() write into the slot that store() then overwrote.  Any order must work."""
+    from finenvs_b200.agents.PPO.buffer import Buffer
+
+    N, W, T = 3000, 8, 5
+    env, twin = _twin_envs(N, W)
+    states, twin_states = env.reset(), twin.reset()     # reset FIRST (plain tensor) ...
+    buf = Buffer(2, 0.99, 0, capacity=T)
+    buf.bind_env(env)                                   # ... then bind
+    _rollouts_match_twin(env, twin, buf, states, twin_states, N, W, T)
+
+
+def test_bind_env_mid_rollout_and_capacity_growth():
+    from finenvs_b200.agents.PPO.buffer import Buffer
+
+    N, W, T = 1000, 8, 7
+    env, twin = _twin_envs(N, W)
+    states, twin_states = env.reset(), twin.reset()
+    buf = Buffer(2, 0.99, 0, capacity=2)                # grows twice inside the first rollout
+    g = torch.Generator(device="cuda").manual_seed(9)
+    kept = []
+    for t in range(T):
+        if t == 3:
+            buf.bind_env(env)                           # mid-rollout, agent holds an unbound observation
+        actions = torch.rand((N, 1), generator=g, device="cuda") * 2 - 1
+        nxt, rewards, dones, _ = env.step(actions)
+        twin_nxt, _, _, _ = twin.step(actions)
+        buf.store(states, actions, rewards, dones, actions, rewards.unsqueeze(-1))
+        kept.append(twin_states)
+        assert torch.equal(nxt, twin_nxt), t
+        states, twin_states = nxt, twin_nxt
+    buf.prepare_training_data(torch.zeros(N, 1, device="cuda"))
+    assert torch.equal(buf.container["states"].view(T, N, W, 5), torch.stack(kept))
+
+
+@pytest.mark.parametrize("N,W", [(3001, 3), (7, 390 // 6), (18949, 30)])   # tile / tile / pipe kernels
+def test_bound_env_with_slots_that_are_not_16_byte_multiples(N, W):
+    """slot k of the states storage started at k*N*W*5*4 bytes; with odd N (the reference's default is D+1
+    envs) every other slot was misaligned for the kernels' 16-byte stores (FE_EALIGN).  Slot strides are padded now."""
+    from finenvs_b200.agents.PPO.buffer import Buffer
+
+    assert (N * W * 5 * 4) % 16 != 0
+    T = 4
+    env, twin = _twin_envs(N, W, bars=W + 25, days=12)
+    buf = Buffer(2, 0.99, 0, capacity=T)
+    buf.bind_env(env)
+    states, twin_states = env.reset(), twin.reset()
+    assert states.data_ptr() % 16 == 0
+    _rollouts_match_twin(env, twin, buf, states, twin_states, N, W, T, rollouts=2)
+
+
+def test_two_steps_without_a_store_do_not_alias():
+    from finenvs_b200.agents.PPO.buffer import Buffer
+
+    N, W = 2000, 8
+    env, twin = _twin_envs(N, W)
+    buf = Buffer(2, 0.99, 0, capacity=4)
+    buf.bind_env(env)
+    env.reset(), twin.reset()
+    a = torch.zeros((N, 1), device="cuda")
+    o1, _, _, _ = env.step(a)
+    t1, _, _, _ = twin.step(a)
+    o2, _, _, _ = env.step(a)                           # no store in between: must not overwrite o1
+    t2, _, _, _ = twin.step(a)
+    assert o1.data_ptr() != o2.data_ptr()
+    assert torch.equal(o1, t1) and torch.equal(o2, t2)
