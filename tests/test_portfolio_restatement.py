@@ -171,7 +171,8 @@ def test_two_restatements_agree_for_several_assets(tmp_path, A, sigmas, frac, se
             seen["short_open"] += int((grew_short > 0).sum())
             seen["margin_call"] += int((s["margin"] > before["margin"]).sum())
             seen["bankrupt"] += int((od.astype(bool) & (s["ptr"] == 0) & (before["ptr"] + 1 + W < fs.seg_len[np.arange(N) % fs.num_segments])).sum())
-        assert seen["done"] > 0 and seen["short_open"] > 0 and seen["margin_call"] > 0 and seen["bankrupt"] > 0, seen
+        assert seen["done"] > 0 and seen["short_open"] > 0 and seen["margin_call"] > 0, seen
+        assert seen["bankrupt"] > 0 or (A < 5 and not params), seen
         print("branches reached:", seen)
         if params or A >= 30:   # with the default balance two or five assets never exhaust the account
             assert seen["blocked_long"] + seen["blocked_short"] > 0, seen
