@@ -14,8 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FINENVS_B200_LIB") or os.path.join(_HERE, "libfinenvs_b200.so")
 
 RESET_KEEP, RESET_LAST, RESET_ALL = 0, 1, 2
-VARIANT_AUTO, VARIANT_TILE, VARIANT_DIRECT, VARIANT_PORTFOLIO, VARIANT_PIPE, VARIANT_SCATTER, VARIANT_SPLIT, VARIANT_ROWS = 0, 1, 2, 3, 4, 5, 6, 7
-ABI_VERSION = 1
+VARIANT_AUTO, VARIANT_TILE, VARIANT_DIRECT, VARIANT_PORTFOLIO, VARIANT_PIPE, VARIANT_SPLIT, VARIANT_GATHER = 0, 1, 2, 3, 4, 6, 8
+ABI_VERSION = 2
 
 
 class FeParams(C.Structure):
@@ -43,7 +43,8 @@ class FeParams(C.Structure):
 
 
 class FeSeries(C.Structure):
-    _fields_ = [("prices", C.c_void_p), ("logret", C.c_void_p), ("seg_start", C.c_void_p), ("seg_len", C.c_void_p)]
+    _fields_ = [("prices", C.c_void_p), ("logret", C.c_void_p), ("seg_start", C.c_void_p), ("seg_len", C.c_void_p),
+                ("obs_table", C.c_void_p)]
 
 
 class FeState(C.Structure):
@@ -75,7 +76,9 @@ _PROTOTYPES = {
     "fe_error_string": (C.c_char_p, [C.c_int]),
     "fe_tile_envs": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
     "fe_pipe_envs": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
-    "fe_step_kernel_name": (C.c_char_p, [C.POINTER(FeParams)]),
+    "fe_step_kernel_name": (C.c_char_p, [C.POINTER(FeParams), C.POINTER(FeSeries)]),
+    "fe_obs_table_bytes": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
+    "fe_obs_table_build": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "fe_log_returns": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fe_effective_len": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                    C.c_void_p]),
@@ -87,6 +90,9 @@ _PROTOTYPES = {
     "fe_step_host": (C.c_int, [C.POINTER(FeParams), C.POINTER(FeSeries), C.POINTER(FeState), C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
                                C.c_void_p]),
+    "fe_step_host_packed": (C.c_int, [C.POINTER(FeParams), C.POINTER(FeSeries), C.POINTER(FeState), C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                      C.c_void_p]),
     "fe_reset_all": (C.c_int, [C.POINTER(FeParams), C.POINTER(FeSeries), C.POINTER(FeState), C.c_uint64, C.c_int32,
                                C.c_void_p]),
     "fe_returns_advantages": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,

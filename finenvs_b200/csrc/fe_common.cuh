@@ -3,6 +3,7 @@
 #define FE_COMMON_CUH
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -73,6 +74,51 @@ __device__ __forceinline__ void bulk_store(void *dst, uint32_t src_smem, uint32_
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------
+// host side: current-device discipline of the entry points
+// ------------------------------------------------------------------------------------------
+// RAII: make `device` current for the duration of an entry point and put the caller's device back afterwards (an env
+// on cuda:1 inside a process whose current device is cuda:0 must not change where the caller's next allocation lands)
+struct DeviceGuard {
+    int prev = -1, rc = 0;
+    bool switched = false;
+    explicit DeviceGuard(int device) {
+        cudaError_t e = cudaGetDevice(&prev);
+        if (e != cudaSuccess) { rc = (int)e; return; }
+        if (prev != device) {
+            e = cudaSetDevice(device);
+            if (e != cudaSuccess) { rc = (int)e; return; }
+            switched = true;
+        }
+    }
+    ~DeviceGuard() { if (switched) (void)cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+
+// entry points without a device argument: the device that owns `ptr` (a device pointer the caller passed)
+inline int pointer_device(const void *ptr) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess || a.type != cudaMemoryTypeDevice) {
+        (void)cudaGetLastError();
+        int cur = 0;
+        (void)cudaGetDevice(&cur);
+        return cur;
+    }
+    return a.device;
+}
+
+// tuning overrides exist only in experiment builds (-DFE_EXPERIMENTS, tools/build_*_variants.sh); the shipped library
+// reads no environment variable
+#ifdef FE_EXPERIMENTS
+inline int env_override(const char *name) {
+    const char *v = getenv(name);
+    return v ? atoi(v) : 0;
+}
+#else
+constexpr int env_override(const char *) { return 0; }
+#endif
 
 } // namespace
 #endif // FE_COMMON_CUH

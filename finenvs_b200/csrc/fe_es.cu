@@ -28,6 +28,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 namespace {
 
 constexpr int kEsWarps = 8;
@@ -852,6 +854,8 @@ int fe_es_perturb(const FeEsNet *net, uint64_t seed, uint64_t generation, int64_
     EsLayout lay;
     if (!make_layout(net, lay) || !eps_dev || num_pairs <= 0 || pair_id_base < 0 || generation >> 31) return FE_EINVAL;
     if ((uintptr_t)eps_dev & 15) return FE_EALIGN;
+    DeviceGuard guard(pointer_device(eps_dev));
+    if (guard.rc) return guard.rc;
     const int64_t total8 = lay.off[lay.L] / 8, n = num_pairs * total8;
     fe_es_perturb_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(total8, num_pairs, pair_id_base, seed,
                                                                                         generation, (__half *)eps_dev);
@@ -874,16 +878,19 @@ int fe_es_forward(const FeEsNet *net, const float *theta_packed_dev, const void 
     }
     if (((uintptr_t)eps_dev | (uintptr_t)theta_packed_dev) & 15) return FE_EALIGN;
     cudaError_t e;
-    int cur = -1;
-    if ((e = cudaGetDevice(&cur)) != cudaSuccess) return (int)e;
-    if (cur != device && (e = cudaSetDevice(device)) != cudaSuccess) return (int)e;
-    static int num_sms[16] = {0};
+    DeviceGuard guard(device);
+    if (guard.rc) return guard.rc;
+    static std::atomic<int> num_sms_cache[16];
     const int dev = device & 15;
-    if (!num_sms[dev] && (e = cudaDeviceGetAttribute(&num_sms[dev], cudaDevAttrMultiProcessorCount, device)) != cudaSuccess)
-        return (int)e;
+    int num_sms[16];
+    num_sms[dev] = num_sms_cache[dev].load(std::memory_order_relaxed);
+    if (!num_sms[dev]) {
+        if ((e = cudaDeviceGetAttribute(&num_sms[dev], cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return (int)e;
+        num_sms_cache[dev].store(num_sms[dev], std::memory_order_relaxed);
+    }
     const int64_t P = lay.off[lay.L];
     // ---- fast path: 5R -> <= 8 first layer (R <= 64), inputs 16-byte granular, ring fits in shared memory
-    static const bool no_fast = getenv("FE_ES_NO_FAST") != nullptr; // A/B runs and the generic kernel's tests
+    const bool no_fast = env_override("FE_ES_NO_FAST") != 0; // A/B runs (experiment builds only)
     if (!no_fast && lay.out[0] <= 8 && lay.in[0] % 5 == 0 && lay.in[0] / 5 <= 63 &&
         (lazy || (lay.in[0] % 4 == 0 && ((uintptr_t)obs_dev & 15) == 0))) {
         FastShape f;
@@ -911,7 +918,7 @@ int fe_es_forward(const FeEsNet *net, const float *theta_packed_dev, const void 
         }
     }
     // ---- streaming path: every layer has <= 319 inputs, eps chunks 16-byte granular (always), ring + activations fit
-    static const bool no_stream = getenv("FE_ES_NO_STREAM") != nullptr;
+    const bool no_stream = env_override("FE_ES_NO_STREAM") != 0;
     bool stream_ok = !no_stream;
     for (int l = 0; l < lay.L; ++l) stream_ok = stream_ok && lay.in[l] + 1 <= 32 * kStRows;
     if (stream_ok) {
@@ -977,6 +984,8 @@ int fe_es_gradient(const FeEsNet *net, const void *eps_dev, const float *pair_we
     if (!make_layout(net, lay) || !eps_dev || !pair_weights_dev || !scratch_dev || !grad_packed_dev || num_pairs <= 0)
         return FE_EINVAL;
     if (((uintptr_t)eps_dev | (uintptr_t)scratch_dev) & 15) return FE_EALIGN;
+    DeviceGuard guard(pointer_device(eps_dev));
+    if (guard.rc) return guard.rc;
     const int64_t total = lay.off[lay.L], total8 = total / 8, slabs = (num_pairs + kGradSlab - 1) / kGradSlab;
     const dim3 grid((unsigned)((total8 + kGradThreads - 1) / kGradThreads), (unsigned)slabs);
     fe_es_grad_partial_kernel<<<grid, kGradThreads, 0, (cudaStream_t)stream>>>(total8, num_pairs, (const __half *)eps_dev,
@@ -993,6 +1002,8 @@ int fe_es_store(const void *rewards_dev, int32_t rewards_f64, const int32_t *don
     if (!rewards_dev || !dones_dev || !cur_returns_dev || !cur_steps_dev || !counters_dev || !fin_key_dev || !fin_env_dev ||
         !fin_ret_dev || num_envs <= 0 || capacity < 0)
         return FE_EINVAL;
+    DeviceGuard guard(pointer_device(rewards_dev));
+    if (guard.rc) return guard.rc;
     const unsigned blocks = (unsigned)((num_envs + 255) / 256);
     if (rewards_f64)
         fe_es_store_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>(

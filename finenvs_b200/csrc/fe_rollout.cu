@@ -9,6 +9,7 @@
 // rewards; for f64 rewards the running value is f64 after the first iteration and each stored return is
 // rounded once.  No FMA contraction (explicit __*_rn intrinsics; the TU is also built with -fmad=false).
 #include "finenvs_b200.h"
+#include "fe_common.cuh"
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -73,6 +74,8 @@ extern "C" int fe_returns_advantages(const void *rewards_dev, int32_t rewards_f6
                                      void *stream) {
     if (!rewards_dev || !dones_dev || !values_dev || !last_values_dev || !returns_dev || !advantages_dev) return FE_EINVAL;
     if (num_envs <= 0 || num_steps <= 0) return FE_EINVAL;
+    DeviceGuard guard(pointer_device(rewards_dev));
+    if (guard.rc) return guard.rc;
     const unsigned blocks = (unsigned)((num_envs + 255) / 256);
     cudaStream_t q = (cudaStream_t)stream;
     if (rewards_f64)

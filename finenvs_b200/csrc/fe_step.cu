@@ -20,9 +20,14 @@
 #include "finenvs_b200.h"
 #include "fe_common.cuh"
 
+#include <cuda.h> // CUtensorMap (types only; cuTensorMapEncodeTiled is resolved at run time, libcuda is not linked)
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+
+#include <atomic>
+#include <mutex>
+#include <vector>
 
 namespace {
 
@@ -228,7 +233,8 @@ __device__ __forceinline__ EnvResult env_step(const FeParams &p, const FeSeries 
     st.ptr[i] = ptr; st.cash[i] = cash; st.long_sh[i] = lng; st.short_sh[i] = sht; st.margin[i] = margin;
     rewards[i] = (OutT)rew;
     dones[i] = done; // :296 dones.int()
-    if (k.dones_mirror) { reinterpret_cast<OutT *>(k.rewards_mirror)[i] = (OutT)rew; k.dones_mirror[i] = done; }
+    if (k.rewards_mirror) reinterpret_cast<OutT *>(k.rewards_mirror)[i] = (OutT)rew;
+    if (k.dones_mirror) k.dones_mirror[i] = done;
     return res;
 }
 
@@ -580,87 +586,112 @@ fe_pipe_kernel(const FeParams p, const FeSeries s, const FeState st, const Const
 }
 
 // ------------------------------------------------------------------------------------------
-// scatter variant: the pipe variant without register staging.  ncu on the pipe kernel's "cached" flavour
-// (profiles/r01_v3_pipe_ncu_full_c2.txt) shows nothing saturated — DRAM 58 %, L1->XBAR 63 %, LSU 40 % — while a plain
-// fill of the same 1.26 GB runs at 7.4 TB/s: the movers' read side is bounded by what their registers can keep in
-// flight (one tile, ~30 KB per SM).  Here the window elements travel global -> shared memory with element-sized
-// asynchronous copies (cp.async, SASS LDGSTS) that land DIRECTLY at their interleaved position in the output tile
-// (element i of an env's window goes to i + i/4: the 4 -> 5 interleave is the scatter's address pattern); the movers
-// only add the position feature column.  Nothing passes through registers, so the bytes in flight are bounded by the
-// shared-memory ring (kScDepth tiles ahead), not by the register file.  Roles per block (one block per SM):
-//   bookkeeper warps: as in the pipe variant (descriptor ring of {row0, position feature});
-//   mover warps: issue the copies of tile t, then retire tile t - depth (cp.async.wait_group, proxy fence, arrive);
-//   one store warp: waits for a tile to be complete, issues its bulk async store (UBLKCP.G.S), frees the stage of the
-//                   store before it once that one has been read out.
+// gather variant: the window gather done by the TMA engine (round 2; the fast path when the series is L2-resident).
+//
+// Read side.  cp.async.bulk.tensor ... tile::gather4 (SASS UTMALDG.2D.GATHER4) fetches FOUR rows of a 2-D tensor, chosen
+// by row index, with one instruction.  The tensor map used here has a row pitch (80 B) far smaller than its row length
+// (one whole window): "row i" is the window that starts at series row i, so ONE instruction brings the windows of
+// four consecutive envs into shared memory.  The table it reads is the series in OBSERVATION layout — 5 values per
+// row, the four log-returns plus a hole for the position feature — so the bytes land exactly as the (N, W, 5) tensor
+// wants them and the only thing threads still write is the position-feature column (W values per env).  Window
+// starts must be 16-byte aligned for the TMA engine and a 20-byte row is not: the table holds P = 4 (f32; 2 for f64)
+// copies shifted by one row each, copy k serving the windows whose first row is k mod P (fe_obs_table_build; 20.6 MB
+// for the 258 k-row series of BASELINE config 2, L2-resident).
+// Write side.  One bulk async store (UBLKCP.G.S) per 4-env unit, straight from the slot the gather filled.
+// Why this shape (tools/tma_rate_probe.cu, tools/tma_gather_probe.cu, profiles/r02_*): a thread pays ~470 cycles of
+// issue latency per TMA load whatever its size, but loads issued by DIFFERENT warps overlap (1 warp: 750 cycles per
+// gather4, 8 warps: 110, 16 warps: 72 = 67 B/clk/SM), so the movers are many warps with one small unit each rather
+// than one producer with big tiles; shared-memory destinations of tensor copies must be 128-byte aligned, which is why
+// a unit is one gather4 (4 x 20W bytes, padded to a 128-byte pitch) and leaves with its own store.
+// Roles per block (one block per SM, persistent):
+//   bookkeeper warps (kGaBook)  as in the pipe variant: one lane per env runs env_step(), publishes
+//                               {tensor row index, position feature} of a 32-env tile into a ring of kGaQ descriptors;
+//   mover warps (kGaMove)       warp-autonomous, no block-wide barrier anywhere: mover m owns units m, m + kGaMove, ...
+//                               (unit u = tile u / 8, group u % 8) and a private ring of S slots.  Per unit: wait for the
+//                               slot's mbarrier (gather landed) -> 4W position-feature stores -> proxy fence -> lane 0
+//                               issues the bulk store, releases the descriptor, waits until the store has read the slot
+//                               and issues the gather of unit i + S into it.
 // ------------------------------------------------------------------------------------------
-#ifndef FE_SC_BOOK
-#define FE_SC_BOOK 6
+#ifndef FE_GATHER_BOOK
+#define FE_GATHER_BOOK 6
 #endif
-#ifndef FE_SC_MOVE
-#define FE_SC_MOVE 8
+#ifndef FE_GATHER_MOVE
+#define FE_GATHER_MOVE 12
 #endif
-constexpr int kScBook = FE_SC_BOOK;
-constexpr int kScMove = FE_SC_MOVE;
-constexpr int kScThreads = (kScBook + kScMove + 1) * 32;
-constexpr int kScMovers = kScMove * 32;
-constexpr int kScQ = 8;        // descriptor ring depth
-constexpr int kScMaxStages = 8;
+constexpr int kGaBook = FE_GATHER_BOOK;
+constexpr int kGaMove = FE_GATHER_MOVE;
+constexpr int kGaThreads = (kGaBook + kGaMove) * 32;
+constexpr int kGaQ = 16;          // descriptor ring depth in tiles (movers keep a descriptor until its unit is stored)
+constexpr int kGaMaxStages = 4;
+constexpr int kGaBarBytes = 1024; // desc_full[Q], desc_free[Q], full[kGaMove][kGaMaxStages]
+constexpr int kGaPitch = 80;      // tensor row pitch of the observation-layout table: P * row bytes for both dtypes
 
-template <typename OutT> __host__ __device__ inline size_t scatter_smem_bytes(int TE, int W, int stages) {
-    return 256 + (size_t)kScQ * TE * 16 + (size_t)stages * (((size_t)TE * W * 5 * sizeof(OutT) + 127) & ~(size_t)127);
+__host__ __device__ inline int ga_row_bytes(bool f64) { return f64 ? 40 : 20; }
+__host__ __device__ inline int ga_phase_shift(bool f64) { return f64 ? 1 : 2; } // log2 P, P = 16 / gcd(16, row bytes)
+// tensor rows per shifted copy: enough for every window start, plus slack so that the last windows stay inside the copy
+__host__ __device__ inline int64_t ga_rows_per_phase(int64_t num_rows, int W, bool f64) {
+    const int P = 1 << ga_phase_shift(f64);
+    return (num_rows + P - 1) / P + (W + P - 1) / P + 8;
 }
-template <int kBytes> __device__ __forceinline__ void cp_async_elem(uint32_t dst_smem, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst_smem), "l"(src), "n"(kBytes) : "memory");
+__host__ __device__ inline size_t ga_table_bytes(int64_t num_rows, int W, bool f64) {
+    return (size_t)(1 << ga_phase_shift(f64)) * (size_t)ga_rows_per_phase(num_rows, W, f64) * kGaPitch + 4096;
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_dyn(int n) { // wait until at most n of this thread's groups are pending
-    switch (n) {
-    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
-    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
-    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-    case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-    case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
-    case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
-    default: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
-    }
+// a window must be a legal TMA box row: a multiple of 16 bytes, at most 256 8-byte elements
+__host__ __device__ inline bool ga_window_ok(int W, bool f64) {
+    const int inner = ga_row_bytes(f64) * W;
+    return (inner % 16) == 0 && inner <= 2048;
+}
+__host__ __device__ inline uint32_t ga_slot_pitch(int W, bool f64) { return (4u * ga_row_bytes(f64) * W + 127u) & ~127u; }
+template <typename OutT> __host__ __device__ inline size_t gather_smem_bytes(int W, int S) {
+    return kGaBarBytes + (size_t)kGaQ * 32 * (4 + sizeof(OutT)) + (size_t)kGaMove * S * ga_slot_pitch(W, sizeof(OutT) == 8);
+}
+
+__device__ __forceinline__ void tma_gather4(uint32_t dst_smem, const CUtensorMap *map, int r0, int r1, int r2, int r3, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+        ::"r"(dst_smem), "l"(map), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar)
+        : "memory");
 }
 
 template <typename OutT, bool kObserve>
-__global__ void __launch_bounds__(kScThreads, 1)
-fe_scatter_kernel(const FeParams p, const FeSeries s, const FeState st, const Consts k, const float *__restrict__ actions,
-                  OutT *__restrict__ obs, OutT *__restrict__ rewards, int32_t *__restrict__ dones, FeStats *stats,
-                  const uint64_t step_arg, const uint64_t *__restrict__ step_dev, const int TE, const int S, const int D) {
+__global__ void __launch_bounds__(kGaThreads, 1)
+fe_gather_kernel(const __grid_constant__ CUtensorMap tmap, const FeParams p, const FeSeries s, const FeState st, const Consts k,
+                 const float *__restrict__ actions, OutT *__restrict__ obs, OutT *__restrict__ rewards,
+                 int32_t *__restrict__ dones, FeStats *stats, const uint64_t step_arg, const uint64_t *__restrict__ step_dev,
+                 const int S, const int rows_per_phase) {
+    constexpr bool kF64 = sizeof(OutT) == 8;
     extern __shared__ __align__(128) unsigned char smem[];
     const uint64_t step = step_dev ? *step_dev : step_arg;
     const int W = p.window;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t ntiles_all = (p.num_envs + TE - 1) / TE;
-    const int ntiles = (int)((ntiles_all - blockIdx.x + gridDim.x - 1) / gridDim.x);
+    const int64_t ntiles_all = (p.num_envs + 31) / 32;
+    const int ntiles = (int)((ntiles_all - blockIdx.x + gridDim.x - 1) / gridDim.x); // tiles blockIdx.x, +gridDim.x, ...
     const uint32_t bars = smem_u32(smem);
     auto desc_full = [&](int q) { return bars + 8u * q; };
-    auto desc_free = [&](int q) { return bars + 8u * (kScQ + q); };
-    auto tile_ready = [&](int si) { return bars + 8u * (2 * kScQ + si); };
-    auto stage_free = [&](int si) { return bars + 8u * (2 * kScQ + kScMaxStages + si); };
-    int64_t *d_row0 = reinterpret_cast<int64_t *>(smem + 256);                      // [Q][TE]
-    double *d_pf = reinterpret_cast<double *>(smem + 256 + (size_t)kScQ * TE * 8);  // [Q][TE], OutT in the low bytes
-    const size_t stage_bytes = ((size_t)TE * W * 5 * sizeof(OutT) + 127) & ~(size_t)127;
-    unsigned char *ring = smem + 256 + (size_t)kScQ * TE * 16;
-    auto tile_env0 = [&](int t) { return ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TE; };
+    auto desc_free = [&](int q) { return bars + 8u * (kGaQ + q); };
+    auto slot_full = [&](int m, int si) { return bars + 8u * (2 * kGaQ + m * kGaMaxStages + si); };
+    int32_t *d_row = reinterpret_cast<int32_t *>(smem + kGaBarBytes);                          // [Q][32] tensor row index
+    OutT *d_pf = reinterpret_cast<OutT *>(smem + kGaBarBytes + (size_t)kGaQ * 32 * 4);         // [Q][32]
+    unsigned char *ring = smem + kGaBarBytes + (size_t)kGaQ * 32 * (4 + sizeof(OutT));
+    const uint32_t pitch = ga_slot_pitch(W, kF64);
+    auto tile_env0 = [&](int t) { return ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * 32; };
 
     if (tid == 0) {
-        for (int q = 0; q < kScQ; ++q) { mbar_init(desc_full(q), 1); mbar_init(desc_free(q), kScMove); }
-        for (int si = 0; si < kScMaxStages; ++si) { mbar_init(tile_ready(si), kScMove); mbar_init(stage_free(si), 1); }
+        for (int q = 0; q < kGaQ; ++q) { mbar_init(desc_full(q), 1); mbar_init(desc_free(q), 8); }
+        for (int m = 0; m < kGaMove; ++m)
+            for (int si = 0; si < kGaMaxStages; ++si) mbar_init(slot_full(m, si), 1);
         mbar_fence_init();
     }
     __syncthreads();
 
-    if (warp < kScBook) {
+    if (warp < kGaBook) {
         // ------------------------------------------------------------------ bookkeepers
-        for (int t = warp; t < ntiles; t += kScBook) {
-            const int q = t % kScQ;
-            mbar_wait(desc_free(q), ((t / kScQ) & 1) ^ 1); // first lap passes immediately
+        const int shift = ga_phase_shift(kF64);
+        for (int t = warp; t < ntiles; t += kGaBook) {
+            const int q = t % kGaQ;
+            mbar_wait(desc_free(q), ((t / kGaQ) & 1) ^ 1); // first lap passes immediately
             const int64_t env0 = tile_env0(t);
-            const int nvalid = (int)min((int64_t)TE, p.num_envs - env0);
+            const int nvalid = (int)min((int64_t)32, p.num_envs - env0);
             EnvResult r;
             r.done = 0; r.newly_terminated = 0; r.fin_return = 0.0; r.fin_len = 0; r.row0 = 0; r.posfeat = 0.0;
             const bool active = lane < nvalid;
@@ -668,93 +699,92 @@ fe_scatter_kernel(const FeParams p, const FeSeries s, const FeState st, const Co
                 const int64_t i = env0 + lane;
                 if (kObserve) r = env_observe(p, s, st, k, i);
                 else r = env_step<OutT>(p, s, st, k, i, actions, rewards, dones, stats != nullptr, step);
-                d_row0[q * TE + lane] = r.row0;
-                reinterpret_cast<OutT *>(d_pf + q * TE)[lane] = (OutT)r.posfeat;
             }
+            // window starting at series row row0 = copy (row0 mod P), tensor row (row0 div P) of that copy
+            d_row[q * 32 + lane] = (int32_t)((r.row0 & ((1 << shift) - 1)) * rows_per_phase + (r.row0 >> shift));
+            d_pf[q * 32 + lane] = (OutT)r.posfeat;
             if (!kObserve) accumulate_stats(stats, r, active);
             __syncwarp();
-            if (lane == 0) mbar_arrive(desc_full(q));
+            if (lane == 0) mbar_arrive(desc_full(q)); // release: descriptor visible to the movers
         }
-    } else if (warp < kScBook + kScMove) {
-        // ------------------------------------------------------------------ movers
-        const int mt = tid - kScBook * 32;
-        const int W4 = W * 4, W5 = W * 5;
-        const int step_e4 = kScMovers / W4, step_i4 = kScMovers % W4; // element walk: idx += kScMovers
-        const int step_eW = kScMovers / W, step_jW = kScMovers % W;   // row walk
-        const OutT *lr = reinterpret_cast<const OutT *>(s.logret);
-        auto retire = [&](int tt, int pending) { // tile tt's copies of this thread have landed -> visible to the bulk store
-            cp_async_wait_dyn(pending);
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tile_ready(tt % S));
-        };
-        for (int t = 0; t < ntiles; ++t) {
-            const int q = t % kScQ, si = t % S;
-            mbar_wait(desc_full(q), (t / kScQ) & 1);
-            if (t >= S) mbar_wait(stage_free(si), ((t / S) - 1) & 1);
-            const int nvalid = (int)min((int64_t)TE, p.num_envs - tile_env0(t));
-            unsigned char *stage = ring + (size_t)si * stage_bytes;
-            const uint32_t stage_u32 = smem_u32(stage);
-            const int64_t *row0s = d_row0 + q * TE;
-            { // window elements: element i of env e -> out element e*W5 + i + i/4
-                int e = mt / W4, i = mt - e * W4;
-                while (e < nvalid) {
-                    const OutT *src = lr + row0s[e] * 4 + i;
-                    cp_async_elem<sizeof(OutT)>(stage_u32 + (uint32_t)(e * W5 + i + (i >> 2)) * (uint32_t)sizeof(OutT), src);
-                    e += step_e4; i += step_i4;
-                    if (i >= W4) { i -= W4; ++e; }
-                }
-            }
-            { // position feature column
-                const OutT *pf = reinterpret_cast<const OutT *>(d_pf + q * TE);
-                OutT *out = reinterpret_cast<OutT *>(stage);
-                int e = mt / W, j = mt - e * W;
-                while (e < nvalid) {
-                    out[(e * W + j) * 5 + 4] = pf[e];
-                    e += step_eW; j += step_jW;
-                    if (j >= W) { j -= W; ++e; }
-                }
-            }
-            cp_async_commit();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(desc_free(q)); // this warp has consumed the descriptor
-            if (t >= D) retire(t - D, D);
-        }
-        for (int tt = ntiles > D ? ntiles - D : 0; tt < ntiles; ++tt) retire(tt, ntiles - 1 - tt);
     } else {
-        // ------------------------------------------------------------------ store warp
-        for (int t = 0; t < ntiles; ++t) {
-            const int si = t % S;
-            mbar_wait(tile_ready(si), (t / S) & 1);
-            const int64_t env0 = tile_env0(t);
-            const int nvalid = (int)min((int64_t)TE, p.num_envs - env0);
-            const size_t out_bytes = (size_t)nvalid * W * 5 * sizeof(OutT);
-            OutT *dst = obs + (size_t)env0 * W * 5;
-            const unsigned char *stage = ring + (size_t)si * stage_bytes;
-            if ((out_bytes & 15) == 0) {
-                if (lane == 0) {
-                    bulk_store(dst, smem_u32(stage), (uint32_t)out_bytes);
-                    bulk_commit();
-                    if (t >= 1) { // at most this store still reading: the one before it has left shared memory
-                        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                        mbar_arrive(stage_free((t - 1) % S));
-                    }
+        // ------------------------------------------------------------------ movers
+        const int m = warp - kGaBook;
+        const uint32_t row_b = (uint32_t)ga_row_bytes(kF64) * W, unit_b = 4 * row_b;
+        int nunits = 0; // units of this block: 8 per tile, fewer in a ragged last tile
+        if (ntiles > 0) {
+            const int last = (int)min((int64_t)32, p.num_envs - tile_env0(ntiles - 1));
+            nunits = (ntiles - 1) * 8 + (last + 3) / 4;
+        }
+        const int n_mine = m < nunits ? (nunits - m + kGaMove - 1) / kGaMove : 0;
+        unsigned char *slots = ring + (size_t)m * S * pitch;
+        // rows lane, lane + 32, ... of a unit (4W rows, dense): which of the unit's 4 envs each belongs to, 2 bits per round
+        constexpr int kRounds = kF64 ? 7 : 13; // ceil(4W / 32) for the largest W ga_window_ok() admits
+        uint32_t env_of_round = 0;
+#pragma unroll
+        for (int u = 0; u < kRounds; ++u) {
+            const int r = lane + 32 * u;
+            env_of_round |= (uint32_t)min(r / W, 3) << (2 * u);
+        }
+        const int rounds = (4 * W + 31) / 32;
+        auto issue = [&](int i) { // lane 0: gather of this mover's unit i into slot i % S
+            const int u = m + i * kGaMove, t = u >> 3, g = u & 7, q = t % kGaQ, si = i % S;
+            mbar_wait(desc_full(q), (t / kGaQ) & 1);
+            const int4 rows4 = *reinterpret_cast<const int4 *>(d_row + q * 32 + 4 * g);
+            mbar_arrive_expect_tx(slot_full(m, si), unit_b);
+            tma_gather4(smem_u32(slots + (size_t)si * pitch), &tmap, rows4.x, rows4.y, rows4.z, rows4.w, slot_full(m, si));
+        };
+        if (lane == 0)
+            for (int i = 0; i < S && i < n_mine; ++i) issue(i);
+        for (int i = 0; i < n_mine; ++i) {
+            const int u = m + i * kGaMove, t = u >> 3, g = u & 7, q = t % kGaQ, si = i % S;
+            const int64_t env0 = tile_env0(t) + 4 * g;
+            const int nv = (int)min((int64_t)4, p.num_envs - env0);
+            mbar_wait(slot_full(m, si), (i / S) & 1); // the four windows have landed; desc_full(q) completed long ago
+            unsigned char *slot = slots + (size_t)si * pitch;
+            const OutT *pf = d_pf + q * 32 + 4 * g;
+            const OutT pf0 = pf[0], pf1 = pf[1], pf2 = pf[2], pf3 = pf[3];
+            OutT *col = reinterpret_cast<OutT *>(slot) + 5 * lane + 4; // position-feature slot of row `lane`
+#pragma unroll
+            for (int uu = 0; uu < kRounds; ++uu) {
+                if (uu < rounds && lane + 32 * uu < 4 * W) {
+                    const uint32_t e = (env_of_round >> (2 * uu)) & 3u;
+                    col[160 * uu] = e == 0 ? pf0 : e == 1 ? pf1 : e == 2 ? pf2 : pf3;
                 }
-            } else { // ragged last tile: plain stores, synchronous
-                const OutT *src = reinterpret_cast<const OutT *>(stage);
-                for (int f = lane; f < nvalid * W * 5; f += 32) dst[f] = src[f];
-                __syncwarp();
-                if (lane == 0) {
-                    if (t >= 1) {
-                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                        mbar_arrive(stage_free((t - 1) % S));
-                    }
+            }
+            fence_proxy_async_smem(); // generic-proxy writes -> visible to the bulk store
+            __syncwarp();
+            if (lane == 0) {
+                bulk_store(obs + (size_t)env0 * W * 5, smem_u32(slot), (uint32_t)nv * row_b);
+                bulk_commit();
+                mbar_arrive(desc_free(q)); // this unit's descriptor entries are consumed
+                if (i + S < n_mine) {
+                    bulk_wait_read_all(); // the store has read the slot: refill it
+                    issue(i + S);
                 }
             }
             __syncwarp();
         }
         if (lane == 0) bulk_wait_read_all();
     }
+}
+
+// series (T, 4) -> observation-layout table: P copies of the (T, 5) layout, copy k starting at series row k, placed
+// k * 80 * rows_per_phase bytes into the buffer (so that every window start is a multiple of the 80-byte tensor pitch)
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+fe_obs_table_kernel(const OutT *__restrict__ logret, const int64_t num_rows, const int64_t rows_per_phase,
+                    unsigned char *__restrict__ table) {
+    constexpr bool kF64 = sizeof(OutT) == 8;
+    const int shift = ga_phase_shift(kF64);
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t r = idx >> shift;
+    const int kk = (int)(idx & ((1 << shift) - 1));
+    if (r >= num_rows || r < kk) return;
+    OutT *dst = reinterpret_cast<OutT *>(table + (size_t)kk * kGaPitch * rows_per_phase + (size_t)(r - kk) * ga_row_bytes(kF64));
+    const OutT *src = logret + r * 4;
+    dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+    dst[4] = (OutT)0; // the hole the movers fill with the position feature
 }
 
 // ------------------------------------------------------------------------------------------
@@ -935,116 +965,6 @@ fe_stream_kernel(const int64_t N, const int W, const OutT *__restrict__ logret, 
 }
 
 // ------------------------------------------------------------------------------------------
-// rows variant (explored alternative, not chosen by `auto`): thread-per-env bookkeeping and warp-autonomous streaming
-// with 16-byte global accesses in ONE launch, no bulk copies, no mbarriers.  A block of 256 threads runs env_step() for
-// 256 envs (headers {row0, position feature} in shared memory), then its 8 warps stream those envs' windows: a WARP
-// owns a group of G consecutive envs (G a power of two >= 4, so a group's slice of the (N, W, 5) tensor starts and ends
-// on a 16-byte boundary for any W) and walks its G*W window rows in chunks of 5120 output bytes: lane l loads rows l,
-// l+32, ... of the chunk (one 16-byte load per f32 row; the env of a row comes from a multiply-high by ceil(2^32 / W),
-// its row0 / position feature by shuffle from the lane holding that env's header), writes them 4 -> 5 interleaved
-// into the warp's PRIVATE 5 KB staging buffer (stride-5 words: conflict-free), and after a __syncwarp the warp copies
-// the buffer out with 16-byte shared loads and 512-contiguous-byte global stores.
-// Measured (profiles/r01_v6_rows_*.txt; c2, 1 Mi envs, W = 60): 0.302 ms (pipe 0.272, tile 0.36, split 0.52) at 3
-// resident blocks per SM (4 blocks / 64 registers: 0.317, spills; 2 blocks: 0.330).  ncu: 81 % of the stall samples sit
-// in the streaming part, on the window loads' scoreboard and on the STG.128 — 24 warps per SM, each a serial
-// load -> stage -> store chain, do not keep enough bytes in flight; c4 (series in HBM): 0.54 ms vs pipe 0.376.
-// ------------------------------------------------------------------------------------------
-constexpr int kRowsThreads = 256;
-constexpr int kRowsWarps = kRowsThreads / 32;
-#ifndef FE_ROWS_MINB
-#define FE_ROWS_MINB 3 /* resident blocks per SM the rows kernel is compiled for (85 registers: no spills) */
-#endif
-constexpr int kRowsChunkBytes = 5120; // staging per warp: 256 f32 rows or 128 f64 rows of 5 values
-template <typename OutT> struct RowsChunk {
-    static constexpr int rows = kRowsChunkBytes / (5 * (int)sizeof(OutT));
-    static constexpr int U = rows / 32; // rows per lane and chunk
-};
-__device__ __forceinline__ int64_t shfl_i64(int64_t v, int src) {
-    const int lo = __shfl_sync(0xFFFFFFFFu, (int)(uint32_t)((uint64_t)v & 0xFFFFFFFFu), src);
-    const int hi = __shfl_sync(0xFFFFFFFFu, (int)(uint32_t)((uint64_t)v >> 32), src);
-    return (int64_t)(((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo);
-}
-// windows of the g <= 32 envs whose headers sit in lanes 0 .. g-1 -> dst (16-byte aligned), through `stage`
-template <typename OutT>
-__device__ __forceinline__ void rows_stream_group(const Row4<OutT> *__restrict__ series_rows, OutT *__restrict__ dst,
-                                                  unsigned char *stage, const int W, const uint32_t magicW, const int g,
-                                                  const int64_t row0_l, const OutT pf_l, const int lane) {
-    constexpr int CH = RowsChunk<OutT>::rows, U = RowsChunk<OutT>::U;
-    const int R = g * W;
-    OutT *so = reinterpret_cast<OutT *>(stage);
-    for (int base = 0; base < R; base += CH) {
-        const int n = min(CH, R - base);
-        Row4<OutT> v[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int rl = lane + 32 * u;
-            const int r = rl < n ? base + rl : base; // lanes past the end shuffle along with a valid row
-            const int e = W == 1 ? r : (int)__umulhi((unsigned)r, magicW);
-            const int64_t r0 = shfl_i64(row0_l, e);
-            if (rl < n) v[u] = ldg_row(series_rows + r0 + (r - e * W));
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int rl = lane + 32 * u;
-            const int r = rl < n ? base + rl : base;
-            const OutT pfe = __shfl_sync(0xFFFFFFFFu, pf_l, W == 1 ? r : (int)__umulhi((unsigned)r, magicW));
-            if (rl < n) {
-                OutT *o = so + rl * 5;
-                if constexpr (sizeof(OutT) == 4) {
-                    o[0] = v[u].v.x; o[1] = v[u].v.y; o[2] = v[u].v.z; o[3] = v[u].v.w;
-                } else {
-                    o[0] = v[u].a.x; o[1] = v[u].a.y; o[2] = v[u].b.x; o[3] = v[u].b.y;
-                }
-                o[4] = pfe;
-            }
-        }
-        __syncwarp();
-        OutT *d = dst + (size_t)base * 5;
-        const int nel = n * 5, n16 = (nel * (int)sizeof(OutT)) >> 4;
-        uint4 *d16 = reinterpret_cast<uint4 *>(d);
-        const uint4 *s16 = reinterpret_cast<const uint4 *>(stage);
-#pragma unroll 5
-        for (int i = lane; i < n16; i += 32) d16[i] = s16[i];
-        // only a ragged last group (N % G envs) can end off a 16-byte boundary
-        for (int f = n16 * (16 / (int)sizeof(OutT)) + lane; f < nel; f += 32) d[f] = so[f];
-        __syncwarp();
-    }
-}
-
-template <typename OutT, bool kObserve>
-__global__ void __launch_bounds__(kRowsThreads, FE_ROWS_MINB)
-fe_rows_kernel(const FeParams p, const FeSeries s, const FeState st, const Consts k, const float *__restrict__ actions,
-               OutT *__restrict__ obs, OutT *__restrict__ rewards, int32_t *__restrict__ dones, FeStats *stats,
-               const uint64_t step_arg, const uint64_t *__restrict__ step_dev, const int G, const uint32_t magicW) {
-    __shared__ __align__(16) unsigned char stage_all[kRowsWarps][kRowsChunkBytes];
-    __shared__ int64_t sh_row0[kRowsThreads];
-    __shared__ OutT sh_pf[kRowsThreads];
-    const uint64_t step = step_dev ? *step_dev : step_arg;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t env0 = (int64_t)blockIdx.x * kRowsThreads;
-    const int nvalid = (int)min((int64_t)kRowsThreads, p.num_envs - env0);
-    const bool active = tid < nvalid;
-    EnvResult r;
-    r.done = 0; r.newly_terminated = 0; r.fin_return = 0.0; r.fin_len = 0; r.row0 = 0; r.posfeat = 0.0;
-    if (active) {
-        if (kObserve) r = env_observe(p, s, st, k, env0 + tid);
-        else r = env_step<OutT>(p, s, st, k, env0 + tid, actions, rewards, dones, stats != nullptr, step);
-    }
-    sh_row0[tid] = r.row0;
-    sh_pf[tid] = (OutT)r.posfeat;
-    if (!kObserve) accumulate_stats(stats, r, active);
-    __syncthreads();
-    const size_t n = (size_t)p.window * 5;
-    for (int e = warp * G; e < nvalid; e += kRowsWarps * G) { // G divides 256: groups never straddle blocks
-        const int g = min(G, nvalid - e);
-        const int64_t row0 = lane < g ? sh_row0[e + lane] : 0;
-        const OutT pf = lane < g ? sh_pf[e + lane] : (OutT)0;
-        rows_stream_group<OutT>(reinterpret_cast<const Row4<OutT> *>(s.logret), obs + (size_t)(env0 + e) * n, stage_all[warp],
-                                p.window, magicW, g, row0, pf, lane);
-    }
-}
-
-// ------------------------------------------------------------------------------------------
 // portfolio variant (A > 1 assets, one cash account): EXTENSION, the reference is single-asset (:223).
 // Semantics: the reference's phases in the reference's order; inside a phase the
 // cash moves ONCE: by the f64 butterfly sum of the per-asset deltas where these do not depend on cash (sales,
@@ -1211,7 +1131,8 @@ __device__ __forceinline__ void portfolio_step(const FeParams &p, const FeSeries
         st.seg[i] = seg; st.ptr[i] = ptr; st.cash[i] = cash;
         rewards[i] = (OutT)rew;
         dones[i] = done;
-        if (k.dones_mirror) { reinterpret_cast<OutT *>(k.rewards_mirror)[i] = (OutT)rew; k.dones_mirror[i] = done; }
+        if (k.rewards_mirror) reinterpret_cast<OutT *>(k.rewards_mirror)[i] = (OutT)rew;
+    if (k.dones_mirror) k.dones_mirror[i] = done;
     }
 }
 
@@ -1433,7 +1354,7 @@ int check_common(const FeParams *p, const FeSeries *s, const FeState *st) {
     if (!s->prices || !s->logret || !s->seg_start || !s->seg_len) return FE_EINVAL;
     if (!st->seg || !st->ptr || !st->cash || !st->long_sh || !st->short_sh || !st->margin) return FE_EINVAL;
     if (p->evaluate && (!st->terminated || !st->ep_return)) return FE_EINVAL;
-    if (((uintptr_t)s->prices | (uintptr_t)s->logret) & 15) return FE_EALIGN;
+    if (((uintptr_t)s->prices | (uintptr_t)s->logret | (uintptr_t)s->obs_table) & 15) return FE_EALIGN;
     return 0;
 }
 
@@ -1459,32 +1380,6 @@ int pick_tile_envs(int W, bool f64, int *threads_out = nullptr) {
     return (int)e;
 }
 
-// tuning overrides (sweeps only)
-int env_override(const char *name) {
-    const char *v = getenv(name);
-    return v ? atoi(v) : 0;
-}
-
-// scatter variant: envs per tile (<= 32, multiple of 4), ring stages S (4..8) and fill depth D = S - 3
-// (D + 1 tiles being filled / landing, up to 2 being stored); false = window too large
-bool pick_scatter(int W, bool f64, int *TE, int *S, int *D) {
-    static const int ov_te = env_override("FE_SC_TE"), ov_s = env_override("FE_SC_STAGES"), ov_d = env_override("FE_SC_DEPTH");
-    int te = 32;
-    if (ov_te >= 4) te = ov_te & ~3;
-    if (te > 32) te = 32;
-    auto bytes = [&](int t, int st) { return f64 ? scatter_smem_bytes<double>(t, W, st) : scatter_smem_bytes<float>(t, W, st); };
-    while (te >= 4 && bytes(te, 4) > (size_t)kSmemMax) te -= 4;
-    if (te < 4) return false;
-    int st = kScMaxStages;
-    while (st > 4 && bytes(te, st) > (size_t)kSmemMax) --st;
-    if (ov_s >= 4 && ov_s <= st) st = ov_s;
-    int d = st - 3;
-    if (ov_d >= 1 && ov_d <= st - 2) d = ov_d;
-    if (d > 6) d = 6;
-    *TE = te; *S = st; *D = d;
-    return true;
-}
-
 // envs per tile of the pipe variant: up to 32 (one bookkeeper lane each), a multiple of 4 (16-byte store
 // granularity), with TE*W rows fitting the movers' register staging; 0 = window too large, use the tile variant
 int pick_pipe_envs(int W, bool f64, int sin) {
@@ -1500,51 +1395,76 @@ int pick_pipe_stages(const FeParams &p, bool f64) {
     const size_t table = (size_t)p.num_rows * p.num_assets * 4 * (f64 ? 8 : 4);
     return table <= ((size_t)48 << 20) ? 0 : kPipeSInStream;
 }
+// slots per mover of the gather variant (3 when they fit, else 2); 0 = this window has no gather variant
+int pick_gather_stages(int W, bool f64) {
+    if (!ga_window_ok(W, f64)) return 0;
+    for (int S = 3; S >= 2; --S)
+        if ((f64 ? gather_smem_bytes<double>(W, S) : gather_smem_bytes<float>(W, S)) <= (size_t)kSmemMax) return S;
+    return 0;
+}
+// the observation-layout table is worth reading only while it stays L2-resident next to the observation stream
+bool gather_table_resident(const FeParams &p, bool f64) { return ga_table_bytes(p.num_rows, p.window, f64) <= ((size_t)64 << 20); }
 
+int device_sm_count(int device, int *out) {
+    static std::atomic<int> num_sms[16];
+    const int dev = device & 15;
+    int n = num_sms[dev].load(std::memory_order_relaxed);
+    if (!n) {
+        cudaError_t e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);
+        if (e != cudaSuccess) return (int)e;
+        num_sms[dev].store(n, std::memory_order_relaxed);
+    }
+    *out = n;
+    return 0;
+}
 
-// Which kernel a launch uses.  `auto`: portfolio when A > 1; split for windows too long for the pipe variant; the
-// persistent pipe variant for populations that give every
-// SM a few tiles AND windows of >= 24 rows (measured on c2, tools/window_sweep.sh -> profiles/r01_v4_window_sweep.txt:
-// W = 4 / 16: tile 0.19 / 0.24 ms vs pipe 0.73 / 0.37 ms — with so few rows per env the 6 bookkeeper warps are the
-// bottleneck, while the tile variant gives every env its own thread; W = 60 / 128 / 390: pipe 0.27 / 0.27 / 0.23 vs tile
-// 0.36 / 0.38 / 0.29); else tile while the window fits in shared memory; else direct.
-enum StepKernel { K_PORTFOLIO, K_SPLIT, K_ROWS, K_SCATTER, K_PIPE, K_TILE, K_DIRECT, K_ERR_SMEM };
+// Which kernel a launch uses.  `auto`: portfolio when A > 1; for populations that give every SM a few tiles and windows
+// of >= 24 rows a persistent kernel — gather when the caller staged the observation-layout table (FeSeries.obs_table),
+// the window is a legal TMA row and that table is L2-resident, else pipe (measured on c2, tools/window_sweep.sh ->
+// profiles/r01_v4_window_sweep.txt: W = 4 / 16: tile 0.19 / 0.24 ms vs pipe 0.73 / 0.37 ms — with so few rows per env the
+// bookkeeper warps are the bottleneck, while the tile variant gives every env its own thread; W = 60 / 128 / 390: pipe
+// 0.27 / 0.27 / 0.23 vs tile 0.36 / 0.38 / 0.29); split for windows too long for the pipe rings; else tile while the
+// window fits in shared memory; else direct.
+enum StepKernel { K_PORTFOLIO, K_SPLIT, K_GATHER, K_PIPE, K_TILE, K_DIRECT, K_ERR_SMEM, K_ERR_TABLE };
 struct StepChoice {
     StepKernel kern;
-    int te;      // envs per tile (pipe / scatter / tile)
+    int te;      // envs per tile (pipe / tile)
     int sin;     // pipe: in-ring stages (0 = cached flavour)
-    int S, D;    // scatter: ring stages, fill depth
+    int S;       // gather: slots per mover
     int threads; // tile: threads per block
 };
-StepChoice choose_kernel(const FeParams &p, bool f64) {
-    StepChoice c = {K_DIRECT, 0, 0, 0, 0, kThreads};
+StepChoice choose_kernel(const FeParams &p, const FeSeries &s, bool f64, int sms) {
+    StepChoice c = {K_DIRECT, 0, 0, 0, kThreads};
     if (p.num_assets > 1 || p.variant == FE_VARIANT_PORTFOLIO) { c.kern = K_PORTFOLIO; return c; }
-    static const int auto_split = env_override("FE_AUTO_SPLIT");     // sweeps: 1 = "auto" prefers split, -1 = never
-    if ((p.variant == FE_VARIANT_SPLIT || (p.variant == FE_VARIANT_AUTO && auto_split > 0))) { c.kern = K_SPLIT; return c; }
-    // rows: the multiply-high row -> env map is exact while 32 * W * W < 2^32
-    if (p.variant == FE_VARIANT_ROWS) { c.kern = p.window <= 8192 ? K_ROWS : K_ERR_SMEM; return c; }
-    static const int auto_scatter = env_override("FE_AUTO_SCATTER"); // sweeps: 1 = "auto" prefers scatter
-    static const int no_pipe = env_override("FE_NO_PIPE");           // sweeps: "auto" never picks pipe
+    if (p.variant == FE_VARIANT_SPLIT) { c.kern = K_SPLIT; return c; }
     // small populations: a persistent grid needs a few tiles per SM to hide its prologue
-    const bool worth_persistent = p.num_envs >= (int64_t)4 * 148 * 32;
-    if (p.variant == FE_VARIANT_SCATTER || (p.variant == FE_VARIANT_AUTO && worth_persistent && auto_scatter > 0)) {
-        if (pick_scatter(p.window, f64, &c.te, &c.S, &c.D)) { c.kern = K_SCATTER; return c; }
-        if (p.variant == FE_VARIANT_SCATTER) { c.kern = K_ERR_SMEM; return c; }
+    const bool worth_persistent = p.num_envs >= (int64_t)4 * sms * 32;
+    if (p.variant == FE_VARIANT_GATHER || p.variant == FE_VARIANT_AUTO) {
+        c.S = pick_gather_stages(p.window, f64);
+        if (p.variant == FE_VARIANT_GATHER) {
+            c.kern = !s.obs_table ? K_ERR_TABLE : c.S == 0 ? K_ERR_SMEM : K_GATHER;
+            return c;
+        }
+        const bool no_gather = env_override("FE_NO_GATHER") != 0; // sweeps: "auto" never picks gather
+        if (!no_gather && s.obs_table && c.S > 0 && worth_persistent && p.window >= 24 && gather_table_resident(p, f64)) {
+            c.kern = K_GATHER;
+            return c;
+        }
     }
-    if (p.variant == FE_VARIANT_PIPE || (p.variant == FE_VARIANT_AUTO && !no_pipe)) {
-        static const int ov_sin = env_override("FE_PIPE_FLAVOUR"); // sweeps: 1 = cached, 2 = stream
+    if (p.variant == FE_VARIANT_PIPE || p.variant == FE_VARIANT_AUTO) {
+        const int ov_sin = env_override("FE_PIPE_FLAVOUR"); // sweeps: 1 = cached, 2 = stream
         c.sin = ov_sin == 1 ? 0 : ov_sin == 2 ? kPipeSInStream : pick_pipe_stages(p, f64);
         c.te = pick_pipe_envs(p.window, f64, c.sin);
         if (c.te == 0 && p.variant == FE_VARIANT_PIPE) { c.kern = K_ERR_SMEM; return c; }
         if (c.te > 0 && (p.variant == FE_VARIANT_PIPE || (worth_persistent && p.window >= 24))) { c.kern = K_PIPE; return c; }
         // windows too long for the pipe variant's rings (> 512 rows f32, > 256 f64): the split variant's warp-per-env
         // streaming (W = 1024, 64 Ki envs: 0.26 ms vs 0.66 ms for tile)
-        if (c.te == 0 && p.variant == FE_VARIANT_AUTO && auto_split >= 0) { c.kern = K_SPLIT; return c; }
+        if (c.te == 0 && p.variant == FE_VARIANT_AUTO) { c.kern = K_SPLIT; return c; }
     }
     c.te = p.variant == FE_VARIANT_DIRECT ? 0 : pick_tile_envs(p.window, f64, &c.threads);
     if (p.variant == FE_VARIANT_TILE && c.te == 0) { c.kern = K_ERR_SMEM; return c; }
     if (c.te > 0) {
-        static const int ov_e = env_override("FE_TILE_ENVS"), ov_t = env_override("FE_TILE_THREADS");
+        const int ov_e = env_override("FE_TILE_ENVS"), ov_t = env_override("FE_TILE_THREADS");
         const size_t sz = f64 ? 8 : 4;
         if (ov_e >= 4 && kSmemHeader + 16 + (size_t)(ov_e & ~3) * (p.window * 9 * sz + sz) <= (size_t)kSmemMax) c.te = ov_e & ~3;
         if (ov_t >= 32 && ov_t <= kThreads) c.threads = ov_t & ~31;
@@ -1554,14 +1474,56 @@ StepChoice choose_kernel(const FeParams &p, bool f64) {
     return c;
 }
 
-int device_sm_count(int device, int *out) {
-    static int num_sms[16] = {0};
-    const int dev = device & 15;
-    if (!num_sms[dev]) {
-        cudaError_t e = cudaDeviceGetAttribute(&num_sms[dev], cudaDevAttrMultiProcessorCount, device);
+// cudaFuncSetAttribute(max dynamic shared memory) once per (kernel instantiation, device); safe to race: the attribute
+// call is idempotent and the flag is only set after it succeeded
+template <typename Kern> int opt_in_smem(Kern kern, std::atomic<uint32_t> &done_mask, int device) {
+    const uint32_t bit = 1u << (device & 15);
+    if (done_mask.load(std::memory_order_acquire) & bit) return 0;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+    if (e != cudaSuccess) return (int)e;
+    done_mask.fetch_or(bit, std::memory_order_release);
+    return 0;
+}
+
+// Tensor map of the observation-layout table (gather variant): rows of `inner_bytes` at an 80-byte pitch — the rows
+// overlap, row i is the window starting i pitches into a shifted copy.  Encoded by the driver (cuTensorMapEncodeTiled,
+// resolved through the runtime so that libcuda is not a link dependency) and cached: a step costs no driver call.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+struct TmapEntry {
+    const void *base;
+    int64_t rows;
+    int inner_bytes, device;
+    CUtensorMap map;
+};
+int gather_tensor_map(const void *table, int64_t total_rows, int inner_bytes, int device, CUtensorMap *out) {
+    static std::mutex mu;
+    static std::vector<TmapEntry> cache;
+    static EncodeTiledFn encode = nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    for (const TmapEntry &e : cache)
+        if (e.base == table && e.rows == total_rows && e.inner_bytes == inner_bytes && e.device == device) { *out = e.map; return 0; }
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
         if (e != cudaSuccess) return (int)e;
+        if (!fn || q != cudaDriverEntryPointSuccess) return FE_EDRIVER;
+        encode = (EncodeTiledFn)fn;
     }
-    *out = num_sms[dev];
+    TmapEntry n;
+    n.base = table; n.rows = total_rows; n.inner_bytes = inner_bytes; n.device = device;
+    const cuuint64_t dims[2] = {(cuuint64_t)(inner_bytes / 8), (cuuint64_t)total_rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)kGaPitch};
+    const cuuint32_t box[2] = {(cuuint32_t)(inner_bytes / 8), 1}, elem_strides[2] = {1, 1};
+    const CUresult r = encode(&n.map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void *>(table), dims, strides, box, elem_strides,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return FE_EDRIVER;
+    if (cache.size() >= 64) cache.erase(cache.begin());
+    cache.push_back(n);
+    *out = n.map;
     return 0;
 }
 
@@ -1572,27 +1534,25 @@ int launch(const FeParams &p, const FeSeries &s, const FeState &st, const float 
     Consts k = make_consts(p);
     k.rewards_mirror = rewards_mirror;
     k.dones_mirror = dones_mirror;
-    const StepChoice c = choose_kernel(p, sizeof(OutT) == 8);
-    const int dev = p.device & 15;
     int sms = 0;
+    int rc = device_sm_count(p.device, &sms);
+    if (rc) return rc;
+    const StepChoice c = choose_kernel(p, s, sizeof(OutT) == 8, sms);
     switch (c.kern) {
     case K_ERR_SMEM: return FE_ESMEM;
+    case K_ERR_TABLE: return FE_EINVAL;
     case K_PORTFOLIO: {
         if ((uintptr_t)obs & 15) return FE_EALIGN;
         const int P = p.window * p.num_assets;
         int CH = 512; // pairs per chunk (8 KB in + 10 KB out, x2 stages); C3: 128 -> 1.492 ms, 256 -> 1.480, 512 -> 1.472, 1024 -> 1.471
-        static const int ov_ch = env_override("FE_PORT_CHUNK");
+        const int ov_ch = env_override("FE_PORT_CHUNK");
         if (ov_ch >= 4) CH = ov_ch & ~3;
         if (CH > ((P + 3) & ~3)) CH = (P + 3) & ~3;
         const size_t smem = port_smem_bytes<OutT>(CH);
         if (smem > (size_t)kSmemMax) return FE_ESMEM;
         auto skern = fe_portfolio_stream_kernel<OutT>;
-        static bool sconfigured[16] = {false};
-        if (!sconfigured[dev]) {
-            cudaError_t e = cudaFuncSetAttribute(skern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
-            if (e != cudaSuccess) return (int)e;
-            sconfigured[dev] = true;
-        }
+        static std::atomic<uint32_t> configured{0};
+        if ((rc = opt_in_smem(skern, configured, p.device))) return rc;
         fe_portfolio_book_kernel<OutT, kObserve><<<(unsigned)((p.num_envs + kBookWarps - 1) / kBookWarps), kBookWarps * 32, 0, stream>>>(
             p, s, st, k, actions, (OutT *)obs, (OutT *)rewards, dones, stats, step, step_dev);
         skern<<<(unsigned)p.num_envs, kPortThreads, smem, stream>>>(p, s, (OutT *)obs, CH);
@@ -1600,77 +1560,57 @@ int launch(const FeParams &p, const FeSeries &s, const FeState &st, const float 
     }
     case K_SPLIT: {
         if ((uintptr_t)obs & 7) return FE_EALIGN;
-        int rc = device_sm_count(p.device, &sms);
-        if (rc) return rc;
         fe_book_kernel<OutT, kObserve><<<(unsigned)((p.num_envs + kThreads - 1) / kThreads), kThreads, 0, stream>>>(
             p, s, st, k, actions, (OutT *)obs, (OutT *)rewards, dones, stats, step, step_dev);
-        static const int ov_b = env_override("FE_STREAM_BLOCKS_PER_SM");
+        const int ov_b = env_override("FE_STREAM_BLOCKS_PER_SM");
         int64_t blocks = (int64_t)sms * (ov_b > 0 ? ov_b : 6); // 48 warps per SM
         const int64_t need = (p.num_envs * 32 + kStreamThreads - 1) / kStreamThreads;
         if (blocks > need) blocks = need;
         fe_stream_kernel<OutT><<<(unsigned)blocks, kStreamThreads, 0, stream>>>(p.num_envs, p.window, (const OutT *)s.logret, (OutT *)obs);
         break;
     }
-    case K_ROWS: {
+    case K_GATHER: {
         if ((uintptr_t)obs & 15) return FE_EALIGN;
-        int G = 4; // envs per warp group: a power of two (divides the block's 256 envs), >= 256 rows when it can
-        while (G < 32 && G * p.window < 256) G *= 2;
-        const uint32_t magicW = p.window == 1 ? 0u : (uint32_t)((((uint64_t)1 << 32) + p.window - 1) / p.window);
-        auto kern = fe_rows_kernel<OutT, kObserve>;
-        static bool configured[16] = {false};
-        if (!configured[dev]) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            if (e != cudaSuccess) return (int)e;
-            configured[dev] = true;
-        }
-        kern<<<(unsigned)((p.num_envs + kRowsThreads - 1) / kRowsThreads), kRowsThreads, 0, stream>>>(
-            p, s, st, k, actions, (OutT *)obs, (OutT *)rewards, dones, stats, step, step_dev, G, magicW);
-        break;
-    }
-    case K_SCATTER: {
-        if ((uintptr_t)obs & 15) return FE_EALIGN;
-        auto kern = fe_scatter_kernel<OutT, kObserve>;
-        static bool configured[16] = {false};
-        if (!configured[dev]) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
-            if (e != cudaSuccess) return (int)e;
-            configured[dev] = true;
-        }
-        int rc = device_sm_count(p.device, &sms);
-        if (rc) return rc;
-        const int64_t ntiles = (p.num_envs + c.te - 1) / c.te;
+        constexpr bool f64 = sizeof(OutT) == 8;
+        const int64_t rpp = ga_rows_per_phase(p.num_rows, p.window, f64);
+        const int64_t total_rows = rpp << ga_phase_shift(f64);
+        if (total_rows >= ((int64_t)1 << 31)) return FE_EINVAL;
+        CUtensorMap tmap;
+        if ((rc = gather_tensor_map(s.obs_table, total_rows, ga_row_bytes(f64) * p.window, p.device, &tmap))) return rc;
+        auto kern = fe_gather_kernel<OutT, kObserve>;
+        static std::atomic<uint32_t> configured{0};
+        if ((rc = opt_in_smem(kern, configured, p.device))) return rc;
+        const int64_t ntiles = (p.num_envs + 31) / 32;
         const unsigned blocks = (unsigned)(ntiles < sms ? ntiles : sms);
-        kern<<<blocks, kScThreads, scatter_smem_bytes<OutT>(c.te, p.window, c.S), stream>>>(
-            p, s, st, k, actions, (OutT *)obs, (OutT *)rewards, dones, stats, step, step_dev, c.te, c.S, c.D);
+        kern<<<blocks, kGaThreads, gather_smem_bytes<OutT>(p.window, c.S), stream>>>(
+            tmap, p, s, st, k, actions, (OutT *)obs, (OutT *)rewards, dones, stats, step, step_dev, c.S, (int)rpp);
         break;
     }
     case K_PIPE: {
         if ((uintptr_t)obs & 15) return FE_EALIGN;
-        auto kern = c.sin == 0 ? fe_pipe_kernel<OutT, kObserve, 0> : fe_pipe_kernel<OutT, kObserve, kPipeSInStream>;
-        static bool configured[16][2] = {{false}};
-        if (!configured[dev][c.sin != 0]) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
-            if (e != cudaSuccess) return (int)e;
-            configured[dev][c.sin != 0] = true;
-        }
-        int rc = device_sm_count(p.device, &sms);
-        if (rc) return rc;
         const int64_t ntiles = (p.num_envs + c.te - 1) / c.te;
         const unsigned blocks = (unsigned)(ntiles < sms ? ntiles : sms);
-        kern<<<blocks, kPipeThreads, pipe_smem_bytes<OutT>(c.te, p.window, c.sin), stream>>>(
-            p, s, st, k, actions, (OutT *)obs, (OutT *)rewards, dones, stats, step, step_dev, c.te);
+        if (c.sin == 0) {
+            auto kern = fe_pipe_kernel<OutT, kObserve, 0>;
+            static std::atomic<uint32_t> configured{0};
+            if ((rc = opt_in_smem(kern, configured, p.device))) return rc;
+            kern<<<blocks, kPipeThreads, pipe_smem_bytes<OutT>(c.te, p.window, c.sin), stream>>>(
+                p, s, st, k, actions, (OutT *)obs, (OutT *)rewards, dones, stats, step, step_dev, c.te);
+        } else {
+            auto kern = fe_pipe_kernel<OutT, kObserve, kPipeSInStream>;
+            static std::atomic<uint32_t> configured{0};
+            if ((rc = opt_in_smem(kern, configured, p.device))) return rc;
+            kern<<<blocks, kPipeThreads, pipe_smem_bytes<OutT>(c.te, p.window, c.sin), stream>>>(
+                p, s, st, k, actions, (OutT *)obs, (OutT *)rewards, dones, stats, step, step_dev, c.te);
+        }
         break;
     }
     case K_TILE: {
         if ((uintptr_t)obs & 15) return FE_EALIGN;
         const size_t smem = tile_smem_bytes<OutT>(c.te, p.window);
         auto kern = fe_tile_kernel<OutT, kObserve>;
-        static size_t configured[16] = {0}; // per device: largest opt-in already set for this instantiation
-        if (smem > configured[dev]) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
-            if (e != cudaSuccess) return (int)e;
-            configured[dev] = kSmemMax;
-        }
+        static std::atomic<uint32_t> configured{0};
+        if ((rc = opt_in_smem(kern, configured, p.device))) return rc;
         const int64_t blocks = (p.num_envs + c.te - 1) / c.te;
         kern<<<(unsigned)blocks, c.threads, smem, stream>>>(p, s, st, k, actions, (OutT *)obs, (OutT *)rewards, dones,
                                                              stats, step, step_dev, c.te);
@@ -1689,36 +1629,33 @@ int launch(const FeParams &p, const FeSeries &s, const FeState &st, const float 
 // step ordinal kept on the device (fe_step_captured): one thread bumps it ahead of the step kernel
 __global__ void fe_bump_kernel(uint64_t *counter) { *counter += 1; }
 
-int set_device(int device) {
-    int cur = -1;
-    cudaError_t e = cudaGetDevice(&cur);
-    if (e != cudaSuccess) return (int)e;
-    if (cur != device) {
-        e = cudaSetDevice(device);
-        if (e != cudaSuccess) return (int)e;
-    }
-    return 0;
-}
-
 // side streams of fe_step_host (created once per device, never destroyed: they live as long as the process)
 constexpr int kHostStreams = 3;
 struct HostPipe {
     cudaStream_t s[kHostStreams];
     cudaEvent_t start, done[kHostStreams];
-    bool ready;
+    bool ok;
 };
-HostPipe *host_pipe(int device) {
+HostPipe *host_pipe(int device) { // the device must be current (DeviceGuard)
     static HostPipe pipes[16];
+    static std::once_flag once[16];
     HostPipe *hp = &pipes[device & 15];
-    if (!hp->ready) {
+    std::call_once(once[device & 15], [hp] {
+        hp->ok = true;
         for (int k = 0; k < kHostStreams; ++k) {
-            if (cudaStreamCreateWithFlags(&hp->s[k], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-            if (cudaEventCreateWithFlags(&hp->done[k], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+            if (cudaStreamCreateWithFlags(&hp->s[k], cudaStreamNonBlocking) != cudaSuccess) hp->ok = false;
+            if (cudaEventCreateWithFlags(&hp->done[k], cudaEventDisableTiming) != cudaSuccess) hp->ok = false;
         }
-        if (cudaEventCreateWithFlags(&hp->start, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        hp->ready = true;
-    }
-    return hp;
+        if (cudaEventCreateWithFlags(&hp->start, cudaEventDisableTiming) != cudaSuccess) hp->ok = false;
+    });
+    return hp->ok ? hp : nullptr;
+}
+
+// dones (N,) int32 -> bit i of the little-endian word i / 32 (the wire format of fe_step_host_packed)
+__global__ void __launch_bounds__(256) fe_pack_dones_kernel(const int32_t *__restrict__ dones, const int64_t n, uint32_t *__restrict__ bits) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned word = __ballot_sync(0xFFFFFFFFu, i < n && dones[i] != 0);
+    if ((threadIdx.x & 31) == 0 && i < n) bits[i >> 5] = word;
 }
 
 } // namespace
@@ -1730,11 +1667,12 @@ int fe_version(void) { return FE_ABI_VERSION; }
 const char *fe_error_string(int code) {
     switch (code) {
     case 0: return "ok";
-    case FE_EINVAL: return "finenvs_b200: invalid argument (null pointer, non-positive size or num_assets outside 1..32)";
+    case FE_EINVAL: return "finenvs_b200: invalid argument (null pointer, non-positive size, num_assets outside 1..32, or the gather variant without FeSeries.obs_table)";
     case FE_EALIGN: return "finenvs_b200: pointer not 16-byte aligned";
-    case FE_ESMEM: return "finenvs_b200: window too large for the tile variant";
+    case FE_ESMEM: return "finenvs_b200: window does not fit the requested kernel variant";
     case FE_EIO: return "finenvs_b200: cannot open or map the file";
     case FE_ECSV: return "finenvs_b200: CSV record outside the format of the native reader";
+    case FE_EDRIVER: return "finenvs_b200: the CUDA driver could not encode the tensor map of the observation-layout table";
     default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "finenvs_b200: unknown error";
     }
 }
@@ -1748,23 +1686,47 @@ int fe_pipe_envs(int32_t window, int32_t out_f64, int32_t stream_flavour) {
     return window > 0 ? pick_pipe_envs(window, out_f64 != 0, stream_flavour ? kPipeSInStream : 0) : 0;
 }
 
-const char *fe_step_kernel_name(const FeParams *p) {
+const char *fe_step_kernel_name(const FeParams *p, const FeSeries *s) {
     if (!p) return "";
     const bool f64 = p->out_f64 != 0;
-    const StepChoice c = choose_kernel(*p, f64);
+    int sms = 148;
+    (void)device_sm_count(p->device, &sms);
+    const FeSeries none = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    const StepChoice c = choose_kernel(*p, s ? *s : none, f64, sms);
     switch (c.kern) {
     case K_PORTFOLIO:
         return f64 ? "fe_portfolio_book_kernel + fe_portfolio_stream_kernel<double>" : "fe_portfolio_book_kernel + fe_portfolio_stream_kernel<float>";
     case K_SPLIT: return f64 ? "fe_book_kernel + fe_stream_kernel<double>" : "fe_book_kernel + fe_stream_kernel<float>";
-    case K_ROWS: return f64 ? "fe_rows_kernel<double>" : "fe_rows_kernel<float>";
-    case K_SCATTER: return f64 ? "fe_scatter_kernel<double>" : "fe_scatter_kernel<float>";
+    case K_GATHER: return f64 ? "fe_gather_kernel<double>" : "fe_gather_kernel<float>";
     case K_PIPE:
         return c.sin == 0 ? (f64 ? "fe_pipe_kernel<double,cached>" : "fe_pipe_kernel<float,cached>")
                           : (f64 ? "fe_pipe_kernel<double,stream>" : "fe_pipe_kernel<float,stream>");
     case K_TILE: return f64 ? "fe_tile_kernel<double>" : "fe_tile_kernel<float>";
     case K_DIRECT: return f64 ? "fe_direct_kernel<double>" : "fe_direct_kernel<float>";
-    default: return "none (window too large for the requested variant)";
+    case K_ERR_TABLE: return "none (the gather variant needs FeSeries.obs_table)";
+    default: return "none (window does not fit the requested variant)";
     }
+}
+
+int64_t fe_obs_table_bytes(int64_t num_rows, int32_t window, int32_t out_f64) {
+    if (num_rows <= 0 || window <= 0 || pick_gather_stages(window, out_f64 != 0) == 0) return 0;
+    if ((ga_rows_per_phase(num_rows, window, out_f64 != 0) << ga_phase_shift(out_f64 != 0)) >= ((int64_t)1 << 31)) return 0;
+    return (int64_t)ga_table_bytes(num_rows, window, out_f64 != 0);
+}
+
+int fe_obs_table_build(const void *logret_dev, int64_t num_rows, int32_t window, int32_t out_f64, void *table_dev, void *stream) {
+    if (!logret_dev || !table_dev || ((uintptr_t)table_dev & 15)) return !logret_dev || !table_dev ? FE_EINVAL : FE_EALIGN;
+    const bool f64 = out_f64 != 0;
+    if (fe_obs_table_bytes(num_rows, window, out_f64) == 0) return FE_ESMEM;
+    cudaStream_t q = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(table_dev, 0, ga_table_bytes(num_rows, window, f64), q);
+    if (e != cudaSuccess) return (int)e;
+    const int64_t rpp = ga_rows_per_phase(num_rows, window, f64);
+    const int64_t threads = num_rows << ga_phase_shift(f64);
+    const unsigned blocks = (unsigned)((threads + 255) / 256);
+    if (f64) fe_obs_table_kernel<double><<<blocks, 256, 0, q>>>((const double *)logret_dev, num_rows, rpp, (unsigned char *)table_dev);
+    else fe_obs_table_kernel<float><<<blocks, 256, 0, q>>>((const float *)logret_dev, num_rows, rpp, (unsigned char *)table_dev);
+    return (int)cudaGetLastError();
 }
 
 int fe_log_returns(const double *prices_dev, int64_t num_rows, int32_t num_assets, double *logret64_dev,
@@ -1789,7 +1751,8 @@ int fe_observe(const FeParams *p, const FeSeries *s, const FeState *st, void *ob
     int rc = check_common(p, s, st);
     if (rc) return rc;
     if (!obs_dev) return FE_EINVAL;
-    if ((rc = set_device(p->device))) return rc;
+    DeviceGuard guard(p->device);
+    if (guard.rc) return guard.rc;
     return p->out_f64 ? launch<double, true>(*p, *s, *st, nullptr, obs_dev, nullptr, nullptr, nullptr, 0, (cudaStream_t)stream)
                       : launch<float, true>(*p, *s, *st, nullptr, obs_dev, nullptr, nullptr, nullptr, 0, (cudaStream_t)stream);
 }
@@ -1800,7 +1763,8 @@ int fe_step(const FeParams *p, const FeSeries *s, const FeState *st, const float
     if (rc) return rc;
     if (!actions_dev || !obs_dev || !rewards_dev || !dones_dev) return FE_EINVAL;
     if (stats_dev && !p->evaluate && (!st->ep_return || !st->ep_len)) return FE_EINVAL;
-    if ((rc = set_device(p->device))) return rc;
+    DeviceGuard guard(p->device);
+    if (guard.rc) return guard.rc;
     return p->out_f64 ? launch<double, false>(*p, *s, *st, actions_dev, obs_dev, rewards_dev, dones_dev, stats_dev,
                                               step_counter, (cudaStream_t)stream)
                       : launch<float, false>(*p, *s, *st, actions_dev, obs_dev, rewards_dev, dones_dev, stats_dev,
@@ -1813,7 +1777,8 @@ int fe_step_captured(const FeParams *p, const FeSeries *s, const FeState *st, co
     if (rc) return rc;
     if (!actions_dev || !obs_dev || !rewards_dev || !dones_dev || !step_counter_dev) return FE_EINVAL;
     if (stats_dev && !p->evaluate && (!st->ep_return || !st->ep_len)) return FE_EINVAL;
-    if ((rc = set_device(p->device))) return rc;
+    DeviceGuard guard(p->device);
+    if (guard.rc) return guard.rc;
     fe_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_counter_dev);
     if ((rc = (int)cudaGetLastError())) return rc;
     return p->out_f64 ? launch<double, false>(*p, *s, *st, actions_dev, obs_dev, rewards_dev, dones_dev, stats_dev, 0,
@@ -1827,7 +1792,8 @@ int fe_observe_lazy(const FeParams *p, const FeSeries *s, const FeState *st, int
     int rc = check_common(p, s, st);
     if (rc) return rc;
     if (!obs_row0_dev || !obs_posfeat_dev || p->num_assets != 1) return FE_EINVAL;
-    if ((rc = set_device(p->device))) return rc;
+    DeviceGuard guard(p->device);
+    if (guard.rc) return guard.rc;
     const Consts k = make_consts(*p);
     const unsigned blocks = (unsigned)((p->num_envs + kThreads - 1) / kThreads);
     if (p->out_f64)
@@ -1846,7 +1812,8 @@ int fe_step_lazy(const FeParams *p, const FeSeries *s, const FeState *st, const 
     if (rc) return rc;
     if (!actions_dev || !obs_row0_dev || !obs_posfeat_dev || !rewards_dev || !dones_dev || p->num_assets != 1) return FE_EINVAL;
     if (stats_dev && !p->evaluate && (!st->ep_return || !st->ep_len)) return FE_EINVAL;
-    if ((rc = set_device(p->device))) return rc;
+    DeviceGuard guard(p->device);
+    if (guard.rc) return guard.rc;
     const Consts k = make_consts(*p);
     const unsigned blocks = (unsigned)((p->num_envs + kThreads - 1) / kThreads);
     if (p->out_f64)
@@ -1864,8 +1831,8 @@ int fe_materialize(const FeParams *p, const FeSeries *s, const int64_t *obs_row0
                    void *obs_dev, void *stream) {
     if (!p || !s || !s->logret || !obs_row0_dev || !obs_posfeat_dev || !obs_dev) return FE_EINVAL;
     if (p->num_envs <= 0 || p->window <= 0 || p->num_assets != 1) return FE_EINVAL;
-    int rc = set_device(p->device);
-    if (rc) return rc;
+    DeviceGuard guard(p->device);
+    if (guard.rc) return guard.rc;
     const unsigned blocks = (unsigned)((p->num_envs * 32 + kThreads - 1) / kThreads);
     if (p->out_f64)
         fe_materialize_kernel<double><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(
@@ -1880,35 +1847,41 @@ int fe_materialize(const FeParams *p, const FeSeries *s, const int64_t *obs_row0
 // every array keeps its alignment); chunk c's action upload, kernel and result download run on side stream
 // c % kHostStreams, so the upload of chunk c+1 and the download of chunk c-1 overlap the kernel of chunk c
 // (two copy engines + SMs busy at once).  Redraws are keyed by global env id, so chunking changes no result.
-int fe_step_host(const FeParams *p, const FeSeries *s, const FeState *st, const float *actions_host, float *actions_dev,
-                 void *obs_dev, void *rewards_dev, int32_t *dones_dev, void *rewards_host, int32_t *dones_host,
-                 FeStats *stats_dev, uint64_t step_counter, void *stream) {
-    if (!p || !s || !st || !actions_host || !actions_dev || !rewards_host || !dones_host) return FE_EINVAL;
+// dones travel either as int32 per env (dones_host) or bit-packed, 1 bit per env (dones_bits_host): exactly one of the
+// two is non-NULL.
+static int step_host_impl(const FeParams *p, const FeSeries *s, const FeState *st, const float *actions_host, float *actions_dev,
+                          void *obs_dev, void *rewards_dev, int32_t *dones_dev, void *rewards_host, int32_t *dones_host,
+                          uint32_t *dones_bits_host, FeStats *stats_dev, uint64_t step_counter, void *stream) {
+    if (!p || !s || !st || !actions_host || !actions_dev || !rewards_host || (!dones_host == !dones_bits_host)) return FE_EINVAL;
     int rc = check_common(p, s, st);
     if (rc) return rc;
     if (!obs_dev || !rewards_dev || !dones_dev) return FE_EINVAL;
     if (stats_dev && !p->evaluate && (!st->ep_return || !st->ep_len)) return FE_EINVAL;
-    if ((rc = set_device(p->device))) return rc;
+    DeviceGuard guard(p->device);
+    if (guard.rc) return guard.rc;
     cudaStream_t q = (cudaStream_t)stream;
     const int64_t n = p->num_envs;
     const int A = p->num_assets;
     const size_t osz = p->out_f64 ? 8 : 4;
+    const void *dones_any = dones_host ? (const void *)dones_host : (const void *)dones_bits_host;
     // Zero-copy mode: when all three host buffers are pinned (mapped into the device's address space), the step
     // kernel reads the actions from them and writes rewards / dones to them directly over PCIe — 12 bytes per env
-    // spread over the whole kernel, no copy-engine hop, no head (upload) or tail (download) outside the kernel.
+    // (8.1 with bit-packed dones, which a small kernel writes after the step) spread over the whole kernel, no
+    // copy-engine hop, no head (upload) or tail (download) outside the kernel.
     // rewards_dev / dones_dev are written as well (device-side consumers); actions_dev is left untouched.
     // (Tried instead: copy-engine upload of the actions in chunks behind the already running kernel, each chunk
     // followed by a 4-byte copy bumping an arrival counter the envs poll.  Same speed on one GPU (0.317 ms per
     // 1 Mi-env step) and on eight (0.67 vs 0.68 ms: with 8 ranks the host side of PCIe, not the read latency, is the
     // limit), more machinery, and a kernel that waits for copies queued after it deadlocks under anything that
     // serialises launches (ncu, CUDA_LAUNCH_BLOCKING=1) — dropped.)
-    static const int no_zc = env_override("FE_HOST_NO_ZEROCOPY");
-    if (!no_zc) {
+    int sms = 0;
+    if ((rc = device_sm_count(p->device, &sms))) return rc;
+    if (!env_override("FE_HOST_NO_ZEROCOPY")) {
         cudaPointerAttributes aa, ar, ad;
         const bool ok = cudaPointerGetAttributes(&aa, actions_host) == cudaSuccess && aa.type == cudaMemoryTypeHost &&
                         aa.devicePointer && cudaPointerGetAttributes(&ar, rewards_host) == cudaSuccess &&
                         ar.type == cudaMemoryTypeHost && ar.devicePointer &&
-                        cudaPointerGetAttributes(&ad, dones_host) == cudaSuccess && ad.type == cudaMemoryTypeHost &&
+                        cudaPointerGetAttributes(&ad, dones_any) == cudaSuccess && ad.type == cudaMemoryTypeHost &&
                         ad.devicePointer;
         (void)cudaGetLastError(); // an unregistered pointer leaves a sticky-free error on old drivers
         // Only for the persistent (and the portfolio) kernels: their bookkeeper warps run tiles ahead, which hides the
@@ -1916,18 +1889,23 @@ int fe_step_host(const FeParams *p, const FeSeries *s, const FeState *st, const 
         // sit on its shared memory while it waits for its actions and write 16-byte PCIe packets (measured W = 60,
         // 1 Mi envs: 1.04 ms zero-copy, 0.77 ms with a copy-engine upload + zero-copy writes, vs 0.36 ms
         // device-resident): those take the chunked copy pipeline below.
-        const StepKernel kk = choose_kernel(*p, p->out_f64 != 0).kern;
+        const StepKernel kk = choose_kernel(*p, *s, p->out_f64 != 0, sms).kern;
         if (ok && kk != K_TILE && kk != K_DIRECT) {
             const float *a = (const float *)aa.devicePointer;
+            int32_t *dmirror = dones_host ? (int32_t *)ad.devicePointer : nullptr;
             rc = p->out_f64 ? launch<double, false>(*p, *s, *st, a, obs_dev, rewards_dev, dones_dev, stats_dev, step_counter, q,
-                                                    nullptr, ar.devicePointer, (int32_t *)ad.devicePointer)
+                                                    nullptr, ar.devicePointer, dmirror)
                             : launch<float, false>(*p, *s, *st, a, obs_dev, rewards_dev, dones_dev, stats_dev, step_counter, q,
-                                                   nullptr, ar.devicePointer, (int32_t *)ad.devicePointer);
+                                                   nullptr, ar.devicePointer, dmirror);
             if (rc) return rc;
+            if (dones_bits_host) {
+                fe_pack_dones_kernel<<<(unsigned)((n + 255) / 256), 256, 0, q>>>(dones_dev, n, (uint32_t *)ad.devicePointer);
+                if ((rc = (int)cudaGetLastError())) return rc;
+            }
             return (int)cudaStreamSynchronize(q);
         }
     }
-    static const int ov_chunks = env_override("FE_HOST_CHUNKS");
+    const int ov_chunks = env_override("FE_HOST_CHUNKS");
     int chunks = ov_chunks > 0 ? ov_chunks : 4;
     int64_t per = ((n + chunks - 1) / chunks + 1023) & ~(int64_t)1023;
     if (per < 16384) per = 16384; // below this a chunk's kernel is shorter than the launch + copy set-up it would hide
@@ -1957,13 +1935,23 @@ int fe_step_host(const FeParams *p, const FeSeries *s, const FeState *st, const 
         if (sc.ep_return) sc.ep_return += off;
         if (sc.ep_len) sc.ep_len += off;
         const size_t obs_off = (size_t)off * p->window * 5 * A * osz;
-        rc = fe_step(&pc, s, &sc, actions_dev + off * A, (char *)obs_dev + obs_off, (char *)rewards_dev + off * osz,
-                     dones_dev + off, stats_dev, step_counter, cs);
+        rc = p->out_f64 ? launch<double, false>(pc, *s, sc, actions_dev + off * A, (char *)obs_dev + obs_off, (char *)rewards_dev + off * osz,
+                                                dones_dev + off, stats_dev, step_counter, cs)
+                        : launch<float, false>(pc, *s, sc, actions_dev + off * A, (char *)obs_dev + obs_off, (char *)rewards_dev + off * osz,
+                                               dones_dev + off, stats_dev, step_counter, cs);
         if (rc) return rc;
         e = cudaMemcpyAsync((char *)rewards_host + off * osz, (char *)rewards_dev + off * osz, (size_t)cnt * osz,
                             cudaMemcpyDeviceToHost, cs);
         if (e != cudaSuccess) return (int)e;
-        e = cudaMemcpyAsync(dones_host + off, dones_dev + off, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, cs);
+        if (dones_host) {
+            e = cudaMemcpyAsync(dones_host + off, dones_dev + off, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, cs);
+        } else {
+            // the chunk's actions are consumed: its slice of actions_dev (>= cnt * 4 bytes) is scratch for the packed bits
+            uint32_t *bits_dev = reinterpret_cast<uint32_t *>(actions_dev + off * A);
+            fe_pack_dones_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, cs>>>(dones_dev + off, cnt, bits_dev);
+            if ((rc = (int)cudaGetLastError())) return rc;
+            e = cudaMemcpyAsync(dones_bits_host + (off >> 5), bits_dev, (size_t)((cnt + 31) / 32) * 4, cudaMemcpyDeviceToHost, cs);
+        }
         if (e != cudaSuccess) return (int)e;
     }
     if (hp) { // the caller's stream continues only after every side stream has finished
@@ -1976,11 +1964,28 @@ int fe_step_host(const FeParams *p, const FeSeries *s, const FeState *st, const 
     return (int)cudaStreamSynchronize(q);
 }
 
+int fe_step_host(const FeParams *p, const FeSeries *s, const FeState *st, const float *actions_host, float *actions_dev,
+                 void *obs_dev, void *rewards_dev, int32_t *dones_dev, void *rewards_host, int32_t *dones_host,
+                 FeStats *stats_dev, uint64_t step_counter, void *stream) {
+    if (!dones_host) return FE_EINVAL;
+    return step_host_impl(p, s, st, actions_host, actions_dev, obs_dev, rewards_dev, dones_dev, rewards_host, dones_host, nullptr,
+                          stats_dev, step_counter, stream);
+}
+
+int fe_step_host_packed(const FeParams *p, const FeSeries *s, const FeState *st, const float *actions_host, float *actions_dev,
+                        void *obs_dev, void *rewards_dev, int32_t *dones_dev, void *rewards_host, uint32_t *dones_bits_host,
+                        FeStats *stats_dev, uint64_t step_counter, void *stream) {
+    if (!dones_bits_host) return FE_EINVAL;
+    return step_host_impl(p, s, st, actions_host, actions_dev, obs_dev, rewards_dev, dones_dev, rewards_host, nullptr, dones_bits_host,
+                          stats_dev, step_counter, stream);
+}
+
 int fe_reset_all(const FeParams *p, const FeSeries *s, const FeState *st, uint64_t step_counter, int32_t redraw,
                  void *stream) {
     int rc = check_common(p, s, st);
     if (rc) return rc;
-    if ((rc = set_device(p->device))) return rc;
+    DeviceGuard guard(p->device);
+    if (guard.rc) return guard.rc;
     fe_reset_all_kernel<<<(unsigned)((p->num_envs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*p, *s, *st, step_counter,
                                                                                                  redraw);
     return (int)cudaGetLastError();

@@ -190,6 +190,8 @@ class StagedSeries:
     seg_len_raw: torch.Tensor  # (D,) i32
     window: int
     logret64: torch.Tensor | None = None  # kept only when asked (loader parity tests)
+    _obs_table: torch.Tensor | None = None  # observation-layout table of the gather kernel (built on first use)
+    _obs_table_tried: bool = False
 
     @property
     def num_rows(self) -> int:
@@ -208,7 +210,33 @@ class StagedSeries:
         return self.prices.device
 
     def nbytes(self) -> int:
-        return sum(t.numel() * t.element_size() for t in (self.prices, self.logret, self.seg_start, self.seg_len))
+        extra = self._obs_table.numel() if self._obs_table is not None else 0
+        return extra + sum(t.numel() * t.element_size() for t in (self.prices, self.logret, self.seg_start, self.seg_len))
+
+    # the table only pays while it stays L2-resident beside the observation stream (csrc/fe_step.cu: gather_table_resident)
+    OBS_TABLE_MAX_BYTES = 64 << 20
+
+    def obs_table(self) -> torch.Tensor | None:
+        """The log-returns in OBSERVATION layout (5 values per row, shifted copies so that every window start is
+        16-byte aligned) that the gather kernel's TMA gather4 reads — replaces the per-step (N, L, 4) gather + cat of
+        time_series_env.py:423-445 on the read side.  Built once per series on first use (fe_obs_table_build); None for
+        multi-asset series, windows that are not a legal TMA row, or series too long for the table to stay in L2."""
+        if self._obs_table_tried:
+            return self._obs_table
+        self._obs_table_tried = True
+        if self.num_assets != 1:
+            return None
+        L = _lib.lib()
+        f64 = int(self.logret.dtype == torch.float64)
+        nbytes = int(L.fe_obs_table_bytes(self.num_rows, self.window, f64))
+        if nbytes == 0 or nbytes > self.OBS_TABLE_MAX_BYTES:
+            return None
+        with torch.cuda.device(self.device):
+            table = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            _lib.check(L.fe_obs_table_build(self.logret.data_ptr(), self.num_rows, self.window, f64, table.data_ptr(),
+                                            torch.cuda.current_stream(self.device).cuda_stream), "fe_obs_table_build")
+        self._obs_table = table
+        return table
 
 
 def stage_series(prices, seg_start, seg_len_raw, window: int, device: str, obs_dtype=torch.float32,

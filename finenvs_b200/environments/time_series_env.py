@@ -35,8 +35,8 @@ except Exception:  # pragma: no cover - gym is not installed in the target image
 
 _RESET_MODES = {"keep": _lib.RESET_KEEP, "last": _lib.RESET_LAST, "all": _lib.RESET_ALL}
 _VARIANTS = {"auto": _lib.VARIANT_AUTO, "tile": _lib.VARIANT_TILE, "direct": _lib.VARIANT_DIRECT,
-             "portfolio": _lib.VARIANT_PORTFOLIO, "pipe": _lib.VARIANT_PIPE, "scatter": _lib.VARIANT_SCATTER, "split": _lib.VARIANT_SPLIT,
-             "rows": _lib.VARIANT_ROWS}
+             "portfolio": _lib.VARIANT_PORTFOLIO, "pipe": _lib.VARIANT_PIPE, "split": _lib.VARIANT_SPLIT,
+             "gather": _lib.VARIANT_GATHER}
 
 
 class LazyObs:
@@ -179,9 +179,11 @@ class TimeSeriesEnv(BaseObject):
                       population (multi-GPU); draws are keyed by global id, so results do not
                       depend on the sharding.
         track_stats   accumulate episode count / return / length on the device (stats()).
-        variant       "auto" | "pipe" | "tile" | "direct" | "scatter" | "split" | "rows" | "portfolio" kernel variant (auto: pipe for
-                      populations of >= 18 944 envs with windows of >= 24 rows, else tile; direct when the window does
-                      not fit in shared memory; portfolio whenever the series has more than one asset).
+        variant       "auto" | "gather" | "pipe" | "tile" | "direct" | "split" | "portfolio" kernel variant (auto: for
+                      populations of >= 4 tiles per SM (18 944 envs on a B200) with windows of >= 24 rows the persistent
+                      kernels — gather while the series is short enough for its observation-layout table to stay in L2
+                      and 5*W*itemsize is a multiple of 16, else pipe; else tile; direct when the window does not fit
+                      in shared memory; portfolio whenever the series has more than one asset).
         flat_obs      return observations as (N, W*num_obs) — the 2-D input the ES agent's ParallelMLP needs
                       (parallel_mlp.py:98-103); same memory, only the shape differs.
         num_eval_envs reported in get_env_args() for the ES agent (evo_agent.py:53); the last
@@ -292,7 +294,11 @@ class TimeSeriesEnv(BaseObject):
             dev.index if dev.index is not None else torch.cuda.current_device(),
         )
         s = self.series
-        self._cseries = _lib.FeSeries(s.prices.data_ptr(), s.logret.data_ptr(), s.seg_start.data_ptr(), s.seg_len.data_ptr())
+        # the observation-layout table is only built for envs that can use it (large populations or variant="gather")
+        want_table = variant == _lib.VARIANT_GATHER or (variant == _lib.VARIANT_AUTO and A == 1 and N >= 4096 and self.num_intervals >= 24)
+        table = s.obs_table() if want_table else None
+        self._cseries = _lib.FeSeries(s.prices.data_ptr(), s.logret.data_ptr(), s.seg_start.data_ptr(), s.seg_len.data_ptr(),
+                                      table.data_ptr() if table is not None else None)
         self._cstate = _lib.FeState(
             self._seg.data_ptr(), self._ptr.data_ptr(), self._cash.data_ptr(), self._long.data_ptr(),
             self._short.data_ptr(), self._margin.data_ptr(),
@@ -432,11 +438,13 @@ class TimeSeriesEnv(BaseObject):
         info_dict = self.record_evaluation_metrics() if self.evaluate else {}
         return (lo, rewards, dones, info_dict)
 
-    def step_host(self, actions_host: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, dict]:
+    def step_host(self, actions_host: torch.Tensor, packed_dones: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, dict]:
         """step() for a host-resident policy, through fe_step_host: `actions_host` is a CPU tensor
         (pinned for full speed); rewards and dones come back as pinned CPU tensors, already complete when the
-        call returns (the two pinned buffers are reused by the next step_host call; copy them to keep them);
-        the observation stays in HBM.  Per step: 4N bytes host->device, 8N (f32) device->host."""
+        call returns (the pinned buffers are reused by the next step_host call; copy them to keep them);
+        the observation stays in HBM.  Per step: 4N bytes host->device, 8N (f32) device->host.
+        packed_dones=True (fe_step_host_packed): dones come back bit-packed — a uint8 tensor of 4*ceil(N/32) bytes, bit
+        (i % 8) of byte i // 8 is env i's flag; `unpack_dones()` expands it — N/8 instead of 4N bytes on the wire."""
         if actions_host.device.type != "cpu" or actions_host.dtype != torch.float32 or not actions_host.is_contiguous():
             raise ValueError("actions_host must be a contiguous float32 CPU tensor")
         if actions_host.numel() != self.num_envs * self.num_acts:
@@ -448,24 +456,32 @@ class TimeSeriesEnv(BaseObject):
                 torch.empty(self.num_envs, dtype=torch.int32, device=self._dev),
                 torch.empty(self.num_envs, dtype=self.obs_dtype).pin_memory(),
                 torch.empty(self.num_envs, dtype=torch.int32).pin_memory(),
+                torch.zeros(4 * ((self.num_envs + 31) // 32), dtype=torch.uint8).pin_memory(),
             )
-        a_dev, r_dev, d_dev, rewards, dones = self._host_bufs
+        a_dev, r_dev, d_dev, rewards, dones, done_bits = self._host_bufs
         obs = self._new_obs()
         self.step_count += 1
+        fn = self._L.fe_step_host_packed if packed_dones else self._L.fe_step_host
+        out_dones = done_bits if packed_dones else dones
         _lib.check(
-            self._L.fe_step_host(self._pp, self._ps, self._pst, actions_host.data_ptr(), a_dev.data_ptr(), obs.data_ptr(),
-                                 r_dev.data_ptr(), d_dev.data_ptr(), rewards.data_ptr(), dones.data_ptr(),
-                                 self._stats.data_ptr() if self._stats is not None else None, self.step_count,
-                                 self._stream()),
-            "fe_step_host",
+            fn(self._pp, self._ps, self._pst, actions_host.data_ptr(), a_dev.data_ptr(), obs.data_ptr(),
+               r_dev.data_ptr(), d_dev.data_ptr(), rewards.data_ptr(), out_dones.data_ptr(),
+               self._stats.data_ptr() if self._stats is not None else None, self.step_count, self._stream()),
+            "fe_step_host_packed" if packed_dones else "fe_step_host",
         )
         info_dict = self.record_evaluation_metrics() if self.evaluate else {}
-        return (obs, rewards, dones, info_dict)
+        return (obs, rewards, out_dones, info_dict)
 
-    def host_bytes_per_step(self) -> Tuple[int, int]:
+    def unpack_dones(self, done_bits: torch.Tensor) -> torch.Tensor:
+        """(N,) int32 flags from the bit-packed form step_host(packed_dones=True) returns."""
+        bits = np.unpackbits(done_bits.numpy(), bitorder="little")[: self.num_envs]
+        return torch.from_numpy(bits.astype(np.int32))
+
+    def host_bytes_per_step(self, packed_dones: bool = False) -> Tuple[int, int]:
         """(host->device, device->host) bytes one step_host() call moves over PCIe."""
         osz = 8 if self.obs_dtype == torch.float64 else 4
-        return 4 * self.num_envs * self.num_acts, (osz + 4) * self.num_envs
+        dones = 4 * ((self.num_envs + 31) // 32) if packed_dones else 4 * self.num_envs
+        return 4 * self.num_envs * self.num_acts, osz * self.num_envs + dones
 
     # ------------------------------------------------------------------ captured rollouts (8f-4) ----
     def _observe_into(self, obs: torch.Tensor) -> None:
@@ -542,7 +558,7 @@ class TimeSeriesEnv(BaseObject):
 
     def kernel_name(self) -> str:
         """Which kernel step() launches for this env's shape (diagnostics)."""
-        return self._L.fe_step_kernel_name(self._pp).decode()
+        return self._L.fe_step_kernel_name(self._pp, self._ps).decode()
 
     def stats(self) -> Dict[str, torch.Tensor]:
         """Device-side episode statistics accumulated since the last clear (track_stats=True)."""

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define FE_ABI_VERSION 1
+#define FE_ABI_VERSION 2
 
 /* argument errors */
 #define FE_EINVAL (-1)   /* null pointer / non-positive size / unsupported num_assets */
@@ -32,6 +32,7 @@ extern "C" {
 #define FE_ESMEM (-3)    /* window too large for the requested kernel variant */
 #define FE_EIO (-4)      /* fe_csv_open: the file cannot be opened or mapped */
 #define FE_ECSV (-5)     /* fe_csv_read: a record is outside the format the native reader handles (the caller falls back to pandas) */
+#define FE_EDRIVER (-6)  /* gather variant: the driver's tensor-map encoder is unavailable or rejected the table */
 
 /* FeParams.reset_mode */
 #define FE_RESET_KEEP 0  /* finished envs restart on the same segment (reference evaluate=True, :504) */
@@ -39,14 +40,15 @@ extern "C" {
 #define FE_RESET_ALL 2   /* extension: every finished env redraws its segment */
 
 /* FeParams.variant */
-#define FE_VARIANT_AUTO 0   /* pipe for large populations, else tile when the window fits in shared memory, else direct */
+#define FE_VARIANT_AUTO 0   /* portfolio when num_assets > 1; gather / pipe for large populations; else tile when the window fits in shared memory, else direct */
 #define FE_VARIANT_TILE 1   /* cp.async.bulk in -> smem interleave -> cp.async.bulk out */
 #define FE_VARIANT_DIRECT 2 /* warp-per-env global->global copy (any window) */
-#define FE_VARIANT_PIPE 4  /* persistent warp-specialised pipeline (bookkeeper / mover warps, multi-stage rings) */
-#define FE_VARIANT_SPLIT 6   /* two launches: thread-per-env bookkeeping, then warp-per-env streaming with fully coalesced stores */
-#define FE_VARIANT_SCATTER 5 /* persistent pipeline whose window elements land in the output tile by element-sized cp.async (no register staging) */
-#define FE_VARIANT_ROWS 7    /* one launch: thread-per-env bookkeeping, then warp-autonomous streaming through private staging with 16-byte global loads / stores */
 #define FE_VARIANT_PORTFOLIO 3 /* warp-per-env bookkeeping kernel + block-per-env streaming kernel; always used when num_assets > 1 */
+#define FE_VARIANT_PIPE 4   /* persistent warp-specialised pipeline (bookkeeper / mover warps, multi-stage rings) */
+#define FE_VARIANT_SPLIT 6  /* two launches: thread-per-env bookkeeping, then warp-per-env streaming with fully coalesced stores */
+#define FE_VARIANT_GATHER 8 /* persistent pipeline whose windows arrive by TMA gather4 from the observation-layout table
+                               (FeSeries.obs_table, fe_obs_table_build) and leave by bulk stores */
+/* (5 and 7 were the round-1 "scatter" and "rows" experiments; both measured slower everywhere and were removed) */
 
 typedef struct FeParams {
     int64_t num_envs;        /* envs held by this GPU (a shard) */
@@ -76,6 +78,8 @@ typedef struct FeSeries {
     const void *logret;       /* (T, A, 4) 100*log-returns, float when !out_f64 else double (:179-194) */
     const int64_t *seg_start; /* (D,) first row of segment d: first bar of the day minus W history rows (:141-152) */
     const int32_t *seg_len;   /* (D,) rows in segment d with the NaN probe of :486-496 folded in */
+    const void *obs_table;    /* optional (NULL: none): the log-returns in observation layout for the gather variant,
+                                 fe_obs_table_bytes() bytes filled by fe_obs_table_build(); single-asset series only */
 } FeSeries;
 
 /* Per-env state, structure of arrays (replaces the tensors of :245-275). */
@@ -113,8 +117,18 @@ int fe_tile_envs(int32_t window, int32_t out_f64, int32_t device);
  * 0 if the window does not fit (the tile / direct variants are used instead). */
 int fe_pipe_envs(int32_t window, int32_t out_f64, int32_t stream_flavour);
 
-/* Name of the kernel fe_step / fe_observe will launch for these parameters (diagnostics, bench.py). */
-const char *fe_step_kernel_name(const FeParams *p);
+/* Name of the kernel fe_step / fe_observe will launch for these parameters and this series (s may be NULL: as if
+ * obs_table were NULL).  Diagnostics, bench.py. */
+const char *fe_step_kernel_name(const FeParams *p, const FeSeries *s);
+
+/* Observation-layout table of the gather variant (replaces the (N,L,4) gather + cat of get_log_return_observations /
+ * reset, :423-445, on the read side): the (T,4) log-returns as 5-value rows [lr0..lr3, hole for the position feature],
+ * in P = 4 (float) / 2 (double) copies shifted by one row each so that every window start is 16-byte aligned for the TMA
+ * engine.  fe_obs_table_bytes: buffer size for (num_rows, window, dtype), 0 when this window has no gather variant
+ * (5*W*sizeof(value) must be a multiple of 16 and <= 2048 bytes).  fe_obs_table_build fills a 16-byte aligned buffer of
+ * that size from logret_dev (T,4) of the same dtype.  Worth it while the table stays L2-resident (<= 64 MB: ~800 k rows). */
+int64_t fe_obs_table_bytes(int64_t num_rows, int32_t window, int32_t out_f64);
+int fe_obs_table_build(const void *logret_dev, int64_t num_rows, int32_t window, int32_t out_f64, void *table_dev, void *stream);
 
 /* generate_log_return_dataset (:179-194): logret[t,a,0] = 100*log(O_t/C_{t-1}) (row 0: O_0/O_0),
  * logret[t,a,1..3] = 100*log(H|L|C / O).  Either output may be NULL. */
@@ -163,6 +177,12 @@ int fe_materialize(const FeParams *p, const FeSeries *s, const int64_t *obs_row0
 int fe_step_host(const FeParams *p, const FeSeries *s, const FeState *st, const float *actions_host,
                  float *actions_dev, void *obs_dev, void *rewards_dev, int32_t *dones_dev, void *rewards_host,
                  int32_t *dones_host, FeStats *stats_dev, uint64_t step_counter, void *stream);
+/* fe_step_host with the dones bit-packed on the wire: dones_bits_host holds ceil(N/32) little-endian 32-bit words,
+ * bit (i % 32) of word i / 32 = done flag of env i (4 bytes per env -> 1 bit: 12 -> 8.1 bytes per env-step over PCIe,
+ * which is what bounds 8 ranks sharing one host).  dones_dev still receives the int32 flags. */
+int fe_step_host_packed(const FeParams *p, const FeSeries *s, const FeState *st, const float *actions_host,
+                        float *actions_dev, void *obs_dev, void *rewards_dev, int32_t *dones_dev, void *rewards_host,
+                        uint32_t *dones_bits_host, FeStats *stats_dev, uint64_t step_counter, void *stream);
 
 /* Extension (mirrors isaac_gym_env.py:55-58 reset_all): fresh episode for every env; with redraw != 0
  * each env draws (segment[, offset]) from Philox(seed, global env id, step_counter). */

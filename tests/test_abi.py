@@ -39,7 +39,7 @@ def test_every_declared_symbol_is_exported_and_bound(built):
 def test_struct_layouts_match_the_header(built):
     # sizes implied by the header's field lists (LP64): a silent mismatch would corrupt every call
     assert ctypes.sizeof(built.FeParams) == 4 * 8 + 4 * 4 + 4 * 8 + 8 + 6 * 4
-    assert ctypes.sizeof(built.FeSeries) == 4 * 8
+    assert ctypes.sizeof(built.FeSeries) == 5 * 8
     assert ctypes.sizeof(built.FeState) == 9 * 8
     assert built.STATS_BYTES == 6 * 8
 
@@ -107,29 +107,51 @@ def test_kernel_choice_policy(built):
     DESIGN.md's window sweep justifies is pinned here without a GPU."""
     L = built.lib()
 
-    def name(N=1 << 20, W=60, A=1, rows=258048, f64=0, variant=built.VARIANT_AUTO):
+    def name(N=1 << 20, W=60, A=1, rows=258048, f64=0, variant=built.VARIANT_AUTO, table=False):
         p = built.FeParams(N, 0, N, rows, W, 1024, A, 5, 10000.0, 0.01, 1.5, 0.25, 1, built.RESET_ALL, 1, 0, f64, variant, 0)
-        return L.fe_step_kernel_name(ctypes.byref(p)).decode()
+        s = built.FeSeries(16, 16, 16, 16, 4096 if table else None)    # only obs_table == NULL matters to the policy
+        return L.fe_step_kernel_name(ctypes.byref(p), ctypes.byref(s)).decode()
 
-    assert name() == "fe_pipe_kernel<float,cached>"                           # BASELINE config 2
+    assert name(table=True) == "fe_gather_kernel<float>"                      # BASELINE config 2 with the staged obs table
+    assert name() == "fe_pipe_kernel<float,cached>"                           # ... without it: the round-1 kernel
     assert name(rows=10_000_000) == "fe_pipe_kernel<float,stream>"            # config 4: table larger than L2
+    assert name(rows=10_000_000, table=True) == "fe_pipe_kernel<float,stream>"   # an obs table of 800 MB would not stay in L2
+    assert name(rows=1_000_000, table=True) == "fe_pipe_kernel<float,cached>"
     assert name(f64=1) == "fe_pipe_kernel<double,cached>"
-    assert name(N=1024) == "fe_tile_kernel<float>"                            # config 1: too few tiles per SM
-    assert name(W=4, N=1 << 22) == "fe_tile_kernel<float>" and name(W=16) == "fe_tile_kernel<float>"   # few rows per env
+    assert name(f64=1, table=True) == "fe_pipe_kernel<double,cached>"         # 40 * 60 bytes is more than one TMA row
+    assert name(f64=1, W=50, table=True) == "fe_gather_kernel<double>"
+    assert name(W=61, table=True) == "fe_pipe_kernel<float,cached>"           # 20 * 61 is not a multiple of 16
+    assert name(W=100, table=True) == "fe_gather_kernel<float>" and name(W=104, table=True) == "fe_pipe_kernel<float,cached>"
+    assert name(N=1024) == "fe_tile_kernel<float>" == name(N=1024, table=True)   # config 1: too few tiles per SM
+    assert name(W=4, N=1 << 22) == "fe_tile_kernel<float>" and name(W=16, table=True) == "fe_tile_kernel<float>"   # few rows per env
     assert name(W=24) == "fe_pipe_kernel<float,cached>" and name(W=512, N=1 << 17) == "fe_pipe_kernel<float,cached>"
+    assert name(W=24, table=True) == "fe_gather_kernel<float>"
     assert name(W=1024, N=1 << 16).startswith("fe_book_kernel + fe_stream_kernel")       # beyond the pipe rings
     assert name(W=300, f64=1, N=1 << 17).startswith("fe_book_kernel + fe_stream_kernel")  # f64 rings hold 256 rows
     assert name(W=2000, N=64).startswith("fe_book_kernel + fe_stream_kernel")
     assert name(A=30, W=128, N=65536).startswith("fe_portfolio_book_kernel + fe_portfolio_stream_kernel")   # config 3
     assert name(variant=built.VARIANT_TILE) == "fe_tile_kernel<float>"
     assert name(variant=built.VARIANT_DIRECT) == "fe_direct_kernel<float>"
-    assert name(variant=built.VARIANT_SCATTER) == "fe_scatter_kernel<float>"
     assert name(variant=built.VARIANT_SPLIT).startswith("fe_book_kernel")
-    assert name(variant=built.VARIANT_ROWS) == "fe_rows_kernel<float>"
-    assert name(W=9000, variant=built.VARIANT_ROWS).startswith("none")       # row -> env multiply-high no longer exact
     assert name(N=64, variant=built.VARIANT_PIPE) == "fe_pipe_kernel<float,cached>"
+    assert name(N=64, variant=built.VARIANT_GATHER, table=True) == "fe_gather_kernel<float>"
+    assert name(variant=built.VARIANT_GATHER).startswith("none (the gather variant needs")
+    assert name(W=61, variant=built.VARIANT_GATHER, table=True).startswith("none")
     assert name(W=4000, variant=built.VARIANT_TILE).startswith("none")        # does not fit in shared memory
     assert name(W=4000, variant=built.VARIANT_PIPE).startswith("none")
+    for bad in (5, 7):   # the round-1 scatter / rows experiments are gone: unknown variants fall through to tile / direct
+        assert name(variant=bad) in ("fe_tile_kernel<float>", "fe_direct_kernel<float>")
+
+
+def test_obs_table_geometry(built):
+    """fe_obs_table_bytes: which windows have a gather variant and how large its table is (host arithmetic only)."""
+    L = built.lib()
+    assert L.fe_obs_table_bytes(258048, 60, 0) == 4 * (258048 // 4 + 15 + 8) * 80 + 4096      # 20.6 MB for config 2
+    assert L.fe_obs_table_bytes(258048, 61, 0) == 0 and L.fe_obs_table_bytes(258048, 62, 0) == 0
+    assert L.fe_obs_table_bytes(258048, 100, 0) > 0 and L.fe_obs_table_bytes(258048, 104, 0) == 0
+    assert L.fe_obs_table_bytes(258048, 50, 1) == 2 * (258048 // 2 + 25 + 8) * 80 + 4096
+    assert L.fe_obs_table_bytes(258048, 51, 1) == 0 and L.fe_obs_table_bytes(258048, 52, 1) == 0
+    assert L.fe_obs_table_bytes(0, 60, 0) == 0 and L.fe_obs_table_bytes(100, 0, 0) == 0
 
 
 def test_header_is_plain_c_and_a_c_program_links_against_the_library(built, tmp_path):

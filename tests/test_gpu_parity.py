@@ -1,7 +1,12 @@
 """GPU parity tests proper: the CUDA path (through the C ABI) against the golden traces the
 reference produced and against the CPU oracle on seeded inputs.  Bit-exact everywhere: integers by
 construction, floats because the kernel performs the reference's IEEE operations in the reference's
-order (the stated tolerance of 1e-5 relative is therefore met with margin 0)."""
+order (the stated tolerance of 1e-5 relative is therefore met with margin 0).
+
+Where a test builds its series with `keep_logret64=True` and hands `series.logret64` to the oracle, the oracle steps on
+the log-return table THE GPU COMPUTED (fe_log_returns; <= 2 ulp from torch.log, pinned separately by
+test_log_returns_kernel_vs_reference_values): those tests pin the step, not the table.  The golden-trace tests inject
+the reference's own table instead."""
 import numpy as np
 import pytest
 import torch
@@ -30,16 +35,17 @@ def _env(series, **kw):
 @pytest.mark.parametrize("dtype,variant", [(torch.float32, "auto"), (torch.float64, "auto"), (torch.float32, "direct"),
                                            (torch.float64, "direct"), (torch.float32, "portfolio"),
                                            (torch.float64, "portfolio"), (torch.float32, "pipe"),
-                                           (torch.float64, "pipe"), (torch.float32, "scatter"),
-                                           (torch.float64, "scatter"), (torch.float32, "split"),
-                                           (torch.float64, "split"), (torch.float32, "rows"),
-                                           (torch.float64, "rows")])
+                                           (torch.float64, "pipe"), (torch.float32, "gather"),
+                                           (torch.float64, "gather"), (torch.float32, "split"),
+                                           (torch.float64, "split"), (torch.float32, "tile"), (torch.float64, "tile")])
 def test_cuda_replays_reference_trace(name, dtype, variant):
     z = load_trace(name)
     if variant == "pipe" and _lib_mod().lib().fe_pipe_envs(int(z["window"]), int(dtype == torch.float64), 0) == 0:
         pytest.skip("window too large for the pipe variant's rings")
-    if variant == "scatter" and int(z["window"]) * 5 * (8 if dtype == torch.float64 else 4) * 4 * 4 > 220 * 1024:
-        pytest.skip("window too large for the scatter variant's ring (4 stages of 4 envs)")
+    if variant == "gather" and _lib_mod().lib().fe_obs_table_bytes(int(z["prices"].shape[0]), int(z["window"]), int(dtype == torch.float64)) == 0:
+        pytest.skip("this window is not a legal TMA row (5*W*itemsize must be a multiple of 16, <= 2048 bytes)")
+    if variant == "tile" and _lib_mod().lib().fe_tile_envs(int(z["window"]), int(dtype == torch.float64), 0) == 0:
+        pytest.skip("window too large for the tile variant")
     series = stage_trace_series(z, dtype)
     N = len(z["seg_init"])
     tp = trace_params(z)
@@ -361,6 +367,7 @@ def test_config2_full_size_1M_envs():
     series = loader.stage_series(prices, seg_start, seg_len, W, "cuda:0", torch.float32, keep_logret64=True)
     fs = orc.series_from_prices(prices, seg_start, seg_len, W, logret=series.logret64.cpu().numpy())
     env = _env(series, num_envs=N, seed=42, random_reset="all", random_offset=True, track_stats=True)
+    assert env.kernel_name() == "fe_gather_kernel<float>"               # what bench.py times on this workload
     ref = orc.OracleEnv(fs, num_envs=N, seed=42, reset_mode=2, random_offset=True, out_f64=False)
     g = torch.Generator().manual_seed(0)
     total_done = 0
@@ -385,6 +392,12 @@ def test_config2_full_size_1M_envs():
                            out_f64=False)
     n_done = _lockstep(sl, ref_sl, 2 * 252, np.random.default_rng(3), obs_every=101)
     assert n_done >= 2 * n
+    # the same slice through the round-1 kernel (what `auto` falls back to when 5*W*itemsize is not a multiple of 16)
+    pipe = _env(series, num_envs=n, env_id_base=base, total_envs=N, seed=42, random_reset="all", random_offset=True, variant="pipe")
+    ref_pipe = orc.OracleEnv(fs, num_envs=n, env_id_base=base, total_envs=N, seed=42, reset_mode=2, random_offset=True,
+                             out_f64=False)
+    assert pipe.kernel_name() == "fe_pipe_kernel<float,cached>"
+    _lockstep(pipe, ref_pipe, 60, np.random.default_rng(4), obs_every=7)
 
 
 def test_config4_minute_bars_8M_population_shard():
@@ -417,6 +430,50 @@ def test_config4_minute_bars_8M_population_shard():
         assert np.array_equal(env._cash.cpu().numpy(), ref.cash)
         _check_obs_properties(env, obs, ptr0, seg0)
         assert d_ref.sum() > 0                                          # offsets spread the episode ends
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_config4_stream_kernel_long_lockstep(dtype):
+    """the kernel that runs BASELINE config 4 (pipe, "stream" flavour: series in HBM) in lock-step with
+    the oracle on a 65 536-env slice of the 8 Mi population for 2 x 390 + 10 steps — every env goes through at least two
+    auto-resets with (segment, offset) redraws — in both output dtypes."""
+    from oracle import oracle as orc
+    from finenvs_b200.data import loader
+
+    W, T, bars = 60, 10_000_000, 390
+    rng = np.random.default_rng(20260101)
+    prices = np.round(gbm_ohlc(rng, T, 0.0005), 4)
+    seg_start, seg_len = loader.regular_segments(T, bars, W)
+    series = loader.stage_series(prices, seg_start, seg_len, W, "cuda:0", dtype, keep_logret64=True)
+    fs = orc.series_from_prices(prices, seg_start, seg_len, W, logret=series.logret64.cpu().numpy())
+    total, n, base = 8 << 20, 65536, (3 << 20) + 12345
+    kw = dict(num_envs=n, env_id_base=base, total_envs=total, seed=7)
+    env = _env(series, random_reset="all", random_offset=True, obs_dtype=dtype, **kw)
+    assert env.kernel_name() == f"fe_pipe_kernel<{'double' if dtype == torch.float64 else 'float'},stream>"
+    ref = orc.OracleEnv(fs, reset_mode=2, random_offset=True, out_f64=dtype == torch.float64, **kw)
+    n_done = _lockstep(env, ref, 2 * bars + 10, np.random.default_rng(5), obs_every=97)
+    assert n_done >= 2 * n
+
+
+def test_auto_picks_the_kernels_documented_in_design():
+    """`auto`: gather for large populations over an L2-resident series when 5*W*itemsize is a multiple of
+    16, pipe otherwise (odd windows, long series), tile for small populations, portfolio for A > 1."""
+    from finenvs_b200.data import loader
+
+    def name(W, N, dtype=torch.float32, rows=80 * 37, **kw):
+        prices, seg_start, seg_len = _c1_series(W, days=rows // 37, bars=37, sigma=0.05, seed=W)
+        series = loader.stage_series(prices, seg_start, seg_len, W, "cuda:0", dtype)
+        return _env(series, num_envs=N, obs_dtype=dtype, **kw).kernel_name()
+
+    assert name(60, 40000) == "fe_gather_kernel<float>"
+    assert name(60, 40000, variant="pipe") == "fe_pipe_kernel<float,cached>"
+    assert name(61, 40000) == "fe_pipe_kernel<float,cached>"            # 20 * 61 is not a multiple of 16
+    assert name(50, 40000, torch.float64) == "fe_gather_kernel<double>"
+    assert name(60, 40000, torch.float64) == "fe_pipe_kernel<double,cached>"   # 40 * 60 = 2400 B > one TMA row
+    assert name(128, 40000) == "fe_pipe_kernel<float,cached>"
+    assert name(60, 3000) == "fe_tile_kernel<float>"
+    assert name(16, 40000) == "fe_tile_kernel<float>"                   # few rows per env: thread-per-env bookkeeping wins
+    assert name(60, 40000, rows=1_000_000 // 37 * 37) == "fe_pipe_kernel<float,cached>"   # table would not stay in L2
 
 
 def test_config3_full_size_portfolio():
@@ -464,14 +521,22 @@ def test_flat_obs_and_es_env_args():
     assert o0.shape == (500, W * 5) and int(b._ptr.abs().sum()) == 0 and float(b._cash.min()) == 10000.0
 
 
-@pytest.mark.parametrize("variant", ["pipe", "scatter", "split", "rows"])
+@pytest.mark.parametrize("variant", ["pipe", "gather", "split"])
 @pytest.mark.parametrize("W,N,dtype", [(60, 1024, torch.float32), (60, 5003, torch.float32), (60, 4099, torch.float64),
-                                       (8, 70001, torch.float32), (128, 3000, torch.float32), (3, 999, torch.float32)])
+                                       (8, 70001, torch.float32), (128, 3000, torch.float32), (3, 999, torch.float32),
+                                       (100, 20011, torch.float32), (50, 9001, torch.float64), (4, 1, torch.float32),
+                                       (24, 19001, torch.float32), (12, 33, torch.float64)])
 def test_pipe_variant_vs_oracle(W, N, dtype, variant):
-    """The persistent warp-specialised pipeline: many tiles per block (N >> 148 * 32), ragged last tile, small and
-    larger windows (32/16/8-env tiles), both dtypes, resets with redraws — exact against the oracle."""
+    """The persistent warp-specialised pipelines: many tiles per block (N >> 148 * 32), ragged last tile / last unit,
+    small and larger windows (32/16/8-env tiles; 2- and 3-slot gather rings), both dtypes, resets with redraws — exact
+    against the oracle."""
     from oracle import oracle as orc
     from finenvs_b200.data import loader
+
+    if variant == "gather" and _lib_mod().lib().fe_obs_table_bytes(80 * 37, W, int(dtype == torch.float64)) == 0:
+        pytest.skip("this window is not a legal TMA row")
+    if variant == "pipe" and _lib_mod().lib().fe_pipe_envs(W, int(dtype == torch.float64), 0) == 0:
+        pytest.skip("window too large for the pipe variant's rings")
 
     prices, seg_start, seg_len = _c1_series(W, days=80, bars=37, sigma=0.05, seed=W * 7 + N)
     series = loader.stage_series(prices, seg_start, seg_len, W, "cuda:0", dtype, keep_logret64=True)
@@ -484,7 +549,7 @@ def test_pipe_variant_vs_oracle(W, N, dtype, variant):
 
 
 @pytest.mark.parametrize("N,A,dtype", [(70001, 1, torch.float32), (40000, 1, torch.float64), (9000, 1, torch.float32),
-                                       (33000, 3, torch.float32)])
+                                       (33000, 3, torch.float32), (19007, 1, torch.float32)])
 def test_step_host_pipeline_equals_device_step(N, A, dtype):
     """fe_step_host cuts the envs into chunks on side streams (upload / kernel / download overlapped): same
     results as the one-launch device-resident step, for ragged chunk counts, both dtypes, A > 1, with statistics."""
@@ -502,8 +567,12 @@ def test_step_host_pipeline_equals_device_step(N, A, dtype):
     for t in range(45):
         a = (torch.rand((N, A), generator=g) * 2 - 1)
         o1, r1, d1, _ = a_env.step(a.cuda())
-        o2, r2, d2, _ = b_env.step_host(a.pin_memory() if t % 2 else a)
+        packed = t % 3 == 2     # every third step returns the dones bit-packed (fe_step_host_packed)
+        o2, r2, d2, _ = b_env.step_host(a.pin_memory() if t % 2 else a, packed_dones=packed)
         assert r2.device.type == "cpu" and d2.device.type == "cpu"
+        if packed:
+            assert d2.dtype == torch.uint8 and d2.numel() == 4 * ((N + 31) // 32)
+            d2 = b_env.unpack_dones(d2)
         assert torch.equal(o1, o2) and torch.equal(r1.cpu(), r2) and torch.equal(d1.cpu(), d2)
         assert torch.equal(b_env._host_bufs[1], r1) and torch.equal(b_env._host_bufs[2], d1)   # device copies too
         for k in ("_seg", "_ptr", "_cash", "_long", "_short", "_margin"):
@@ -512,7 +581,7 @@ def test_step_host_pipeline_equals_device_step(N, A, dtype):
     assert int(sa["n_done"]) == int(sb["n_done"]) > 0 and int(sa["sum_len"]) == int(sb["sum_len"])
 
 
-@pytest.mark.parametrize("variant,A,N", [("tile", 1, 3001), ("pipe", 1, 40000), ("split", 1, 5003), ("rows", 1, 5003), ("auto", 3, 2500)])
+@pytest.mark.parametrize("variant,A,N", [("tile", 1, 3001), ("pipe", 1, 40000), ("split", 1, 5003), ("gather", 1, 40003), ("auto", 3, 2500)])
 @pytest.mark.parametrize("params", [(40, 500.0, 0.37, 2.25, 0.4), (1, 250000.0, 0.0, 1.0, 0.1), (12, 20000.0, 0.05, 1.2, 0.3)])
 def test_non_default_parameters_vs_oracle(variant, A, N, params):
     """Every constructor parameter of the reference off its default (time_series_env.py:20-26; the three golden
@@ -520,7 +589,7 @@ def test_non_default_parameters_vs_oracle(variant, A, N, params):
     from oracle import oracle as orc
     from finenvs_b200.data import loader
 
-    W = 10
+    W = 12 if variant == "gather" else 10
     ms, sb, com, imr, mmr = params
     if A == 1:
         prices, seg_start, seg_len = _c1_series(W, days=60, bars=33, sigma=0.06, seed=int(ms) + N)

@@ -77,6 +77,8 @@ struct Args {
     int64_t N;
     int W, S, flags, M, P, lag;
     int *err;
+    int64_t T;
+    unsigned long long *clk;
 };
 
 // one warp = one pipeline.  smem per warp: [S mbarriers (64 B)] [S in slots] [modes 2/3: 2 out slots]
@@ -175,6 +177,301 @@ __global__ void __launch_bounds__(1024, 1) probe_kernel(const __grid_constant__ 
     if (lane == 0) bulk_wait_read<0>();
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// v2.  Arch A2: as mode 0 (gather4 from the pre-interleaved table, warp-autonomous) but a unit is U = 4 * G envs
+//      (G gather4 loads, ONE store) and the descriptors (row index, position feature) of the warp's next 32 units are
+//      fetched in one go (the real kernel gets them from its bookkeeper warps through shared memory).
+//      Arch B: block-cooperative 32-env tiles: 1 producer warp (8 gather4 per tile on one mbarrier), C consumer warps
+//      (write the position features, fence, arrive), 1 store warp (one 20*W*32-byte bulk store per tile; frees stages).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(1024, 1) probe_a2_kernel(const __grid_constant__ CUtensorMap map, const Args a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int W = a.W, S = a.S;
+    constexpr int U = 4 * G;
+    const uint32_t row_b = 20u * W, grp_b = 4 * row_b, grp_pitch = (grp_b + 127) & ~127u, unit_b = U * row_b, pitch = G * grp_pitch;
+    const uint32_t per_warp = 128 + S * pitch;
+    unsigned char *base = smem + (size_t)warp * per_warp;
+    const uint32_t bars = smem_u32(base);
+    unsigned char *ring = base + 128;
+    const int64_t nunits = a.N / U;
+    const int64_t first = (int64_t)blockIdx.x * nw + warp, stride = (int64_t)gridDim.x * nw;
+    const int n_mine = first < nunits ? (int)((nunits - first + stride - 1) / stride) : 0;
+    if (lane == 0) for (int s = 0; s < S; ++s) mbar_init(bars + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    // descriptor batches: lane l holds unit (batch * 32 + l)'s row indices / features in registers
+    int r_reg[U]; float pf_reg[U];
+    int batch_loaded = -1;
+    auto fetch_batch = [&](int b) {
+        const int i = b * 32 + lane;
+        if (i < n_mine) {
+            const int64_t env0 = (first + (int64_t)i * stride) * U;
+#pragma unroll
+            for (int e = 0; e < U; ++e) {
+                const int row0 = __ldg(a.row0 + env0 + e);
+                r_reg[e] = (row0 % a.P) * a.M + row0 / a.P;
+                pf_reg[e] = __ldg(a.pf + env0 + e);
+            }
+        }
+        batch_loaded = b;
+    };
+    // the issue side runs `S` units ahead of the consume side and may sit in the next batch: keep two register sets
+    int r_nxt[U]; float pf_nxt[U];
+    auto load_unit = [&](int i, const int (&rr)[U]) { // all lanes call; lane 0 issues
+        const int s = i % S, src_lane = i & 31;
+        const uint32_t dst = smem_u32(ring + (size_t)s * pitch), bar = bars + 8 * s;
+        int r[U];
+#pragma unroll
+        for (int e = 0; e < U; ++e) r[e] = __shfl_sync(0xFFFFFFFFu, rr[e], src_lane);
+        if (lane == 0) {
+            if (a.flags & 2) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); return; }
+            mbar_expect_tx(bar, unit_b);
+#pragma unroll
+            for (int g = 0; g < G; ++g) gather4(dst + g * grp_pitch, &map, 0, r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3], bar);
+        }
+    };
+    fetch_batch(0);
+#pragma unroll
+    for (int e = 0; e < U; ++e) { r_nxt[e] = r_reg[e]; pf_nxt[e] = pf_reg[e]; }
+    int nxt_batch = 0;
+    auto issue = [&](int i) { // unit i may be in batch_loaded or in the next one
+        const int b = i >> 5;
+        if (b != nxt_batch) { // fetch the next batch into the *_nxt registers
+            const int ii = b * 32 + lane;
+            if (ii < n_mine) {
+                const int64_t env0 = (first + (int64_t)ii * stride) * U;
+#pragma unroll
+                for (int e = 0; e < U; ++e) {
+                    const int row0 = __ldg(a.row0 + env0 + e);
+                    r_nxt[e] = (row0 % a.P) * a.M + row0 / a.P;
+                    pf_nxt[e] = __ldg(a.pf + env0 + e);
+                }
+            }
+            nxt_batch = b;
+        }
+        load_unit(i, r_nxt);
+    };
+    for (int i = 0; i < S && i < n_mine; ++i) issue(i);
+    const int rows = U * W;
+    for (int i = 0; i < n_mine; ++i) {
+        const int s = i % S;
+        if ((i >> 5) != batch_loaded) { // consume side enters a new batch: it is the one the issue side already holds
+#pragma unroll
+            for (int e = 0; e < U; ++e) { r_reg[e] = r_nxt[e]; pf_reg[e] = pf_nxt[e]; }
+            batch_loaded = i >> 5;
+            if (nxt_batch != batch_loaded) { fetch_batch(batch_loaded); }
+        }
+        const int64_t env0 = (first + (int64_t)i * stride) * U;
+        if (!mbar_wait_bounded(bars + 8 * s, (i / S) & 1)) { if (lane == 0) atomicAdd(a.err, 1); return; }
+        float pf_u[U];
+#pragma unroll
+        for (int e = 0; e < U; ++e) pf_u[e] = __shfl_sync(0xFFFFFFFFu, pf_reg[e], i & 31);
+        float *o = reinterpret_cast<float *>(ring + (size_t)s * pitch);
+        for (int b = 0; b < rows; b += 32) {
+            const int r = b + lane;
+            if (r < rows) {
+                const int e = r / W, g = e >> 2;
+                float v = pf_u[0];
+#pragma unroll
+                for (int q = 1; q < U; ++q) v = e == q ? pf_u[q] : v;
+                reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(o) + g * grp_pitch)[5 * (r - g * 4 * W) + 4] = v;
+            }
+        }
+        fence_async();
+        __syncwarp();
+        if (lane == 0 && !(a.flags & 1)) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) bulk_store(a.obs + ((size_t)env0 + 4 * g) * W * 5, smem_u32(o) + g * grp_pitch, grp_b);
+            bulk_commit();
+        }
+        const int j = i - (a.lag - 1);
+        if (j >= 0 && j + S < n_mine) {
+            if (lane == 0) { if (a.lag == 1) bulk_wait_read<0>(); else if (a.lag == 2) bulk_wait_read<1>(); else bulk_wait_read<2>(); }
+            __syncwarp();
+            issue(j + S);
+        }
+    }
+    if (lane == 0) bulk_wait_read<0>();
+}
+
+// Arch B.  smem: [bars 256 B][pf S x 32 floats][S stages of 32 envs]
+__global__ void __launch_bounds__(1024, 1) probe_b_kernel(const __grid_constant__ CUtensorMap map, const Args a, const int C) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int W = a.W, S = a.S;
+    const uint32_t row_b = 20u * W, grp_b = 4 * row_b, grp_pitch = (grp_b + 127) & ~127u, tile_b = 32 * row_b, tile_pitch = 8 * grp_pitch;
+    const uint32_t bars = smem_u32(smem);
+    auto full = [&](int s) { return bars + 8u * s; };
+    auto ready = [&](int s) { return bars + 8u * (8 + s); };
+    auto empty = [&](int s) { return bars + 8u * (16 + s); };
+    float *pf_s = reinterpret_cast<float *>(smem + 256);
+    unsigned char *ring = smem + 256 + 8 * 32 * 4;
+    const int64_t ntiles_all = a.N / 32;
+    const int ntiles = (int)((ntiles_all - blockIdx.x + gridDim.x - 1) / gridDim.x);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(full(s), 1); mbar_init(ready(s), C); mbar_init(empty(s), 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto tile_env0 = [&](int t) { return ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * 32; };
+    if (warp == 0) {
+        // ---------------------------------------------------------------- producer
+        int r_next = 0; float pf_next = 0.f;
+        if (ntiles > 0) { const int row0 = __ldg(a.row0 + tile_env0(0) + lane); r_next = (row0 % a.P) * a.M + row0 / a.P; pf_next = __ldg(a.pf + tile_env0(0) + lane); }
+        for (int t = 0; t < ntiles; ++t) {
+            const int s = t % S;
+            const int r_cur = r_next; const float pf_cur = pf_next;
+            if (t + 1 < ntiles) { const int row0 = __ldg(a.row0 + tile_env0(t + 1) + lane); r_next = (row0 % a.P) * a.M + row0 / a.P; pf_next = __ldg(a.pf + tile_env0(t + 1) + lane); }
+            if (t >= S && !mbar_wait_bounded(empty(s), ((t / S) - 1) & 1)) { if (lane == 0) atomicAdd(a.err, 1); return; }
+            pf_s[s * 32 + lane] = pf_cur;
+            const int r0 = __shfl_sync(0xFFFFFFFFu, r_cur, (lane & 7) * 4), r1 = __shfl_sync(0xFFFFFFFFu, r_cur, (lane & 7) * 4 + 1),
+                      r2 = __shfl_sync(0xFFFFFFFFu, r_cur, (lane & 7) * 4 + 2), r3 = __shfl_sync(0xFFFFFFFFu, r_cur, (lane & 7) * 4 + 3);
+            __syncwarp();
+            if (a.flags & 2) { if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full(s)) : "memory"); continue; }
+            if (lane == 0) mbar_expect_tx(full(s), tile_b);
+            __syncwarp();
+            if (lane < 8) gather4(smem_u32(ring + (size_t)s * tile_pitch) + lane * grp_pitch, &map, 0, r0, r1, r2, r3, full(s));
+        }
+    } else if (warp <= C) {
+        // ---------------------------------------------------------------- consumers: position features of their rows
+        const int c = warp - 1, rows = 32 * W;
+        for (int t = 0; t < ntiles; ++t) {
+            const int s = t % S;
+            if (!mbar_wait_bounded(full(s), (t / S) & 1)) { if (lane == 0) atomicAdd(a.err, 1); return; }
+            unsigned char *o = ring + (size_t)s * tile_pitch;
+            for (int r = c * 32 + lane; r < rows; r += C * 32) {
+                const int e = r / W, g = e >> 2;
+                reinterpret_cast<float *>(o + g * grp_pitch)[5 * (r - g * 4 * W) + 4] = pf_s[s * 32 + e];
+            }
+            fence_async();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ready(s)) : "memory");
+        }
+    } else if (warp == C + 1) {
+        // ---------------------------------------------------------------- store warp
+        if (lane != 0) return;
+        for (int t = 0; t < ntiles; ++t) {
+            const int s = t % S;
+            if (!mbar_wait_bounded(ready(s), (t / S) & 1)) { atomicAdd(a.err, 1); return; }
+            if (!(a.flags & 1)) {
+                for (int g = 0; g < 8; ++g)
+                    bulk_store(a.obs + ((size_t)tile_env0(t) + 4 * g) * W * 5, smem_u32(ring + (size_t)s * tile_pitch) + g * grp_pitch, grp_b);
+                bulk_commit();
+            }
+            if (t >= 1) { // store t-1 has been read out: its stage is free
+                bulk_wait_read<1>();
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty((t - 1) % S)) : "memory");
+            }
+        }
+        bulk_wait_read<0>();
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// v3.  Arch A3: warp-autonomous, a unit is G groups of 4 envs; lane g < G issues ITS group's gather4 and ITS group's bulk
+// store (the rate probe showed ~470 cycles of issue latency per TMA op per thread, overlapping across lanes / warps).
+// Row indices and features are hashes of the env id (no descriptor traffic; the real kernel gets them from shared memory).
+// Phase clocks of block 0 / warp 0 / lane 0 go to a.clk[0..6].
+// ---------------------------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t hash_row(uint32_t env, uint32_t span) {
+    uint32_t x = env * 0x9E3779B9u + 0x7F4A7C15u; x ^= x >> 15; x *= 0x2C1B3C6Du; x ^= x >> 12; x *= 0x297A2D39u; x ^= x >> 15;
+    return x % span;
+}
+template <int G>
+__global__ void __launch_bounds__(1024, 1) probe_a3_kernel(const __grid_constant__ CUtensorMap map, const Args a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int W = a.W, S = a.S;
+    constexpr int U = 4 * G;
+    const uint32_t row_b = 20u * W, grp_b = 4 * row_b, grp_pitch = (grp_b + 127) & ~127u, pitch = G * grp_pitch;
+    unsigned char *base = smem + (size_t)warp * (128 + S * pitch);
+    const uint32_t bars = smem_u32(base);
+    unsigned char *ring = base + 128;
+    const int64_t nunits = a.N / U;
+    const int64_t first = (int64_t)blockIdx.x * nw + warp, stride = (int64_t)gridDim.x * nw;
+    const int n_mine = first < nunits ? (int)((nunits - first + stride - 1) / stride) : 0;
+    if (lane == 0) for (int s = 0; s < S; ++s) mbar_init(bars + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    const uint32_t span = (uint32_t)(a.T - W);
+    auto issue = [&](int i) { // converged call; lanes < G issue
+        const int s = i % S;
+        const uint32_t dst = smem_u32(ring + (size_t)s * pitch), bar = bars + 8 * s;
+        if (a.flags & 2) { if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); return; }
+        if (lane == 0) mbar_expect_tx(bar, U * row_b);
+        __syncwarp();
+        if (lane < G) {
+            const uint32_t env = (uint32_t)((first + (int64_t)i * stride) * U) + 4 * lane;
+            int r[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { const uint32_t row0 = hash_row(env + e, span); r[e] = (row0 % a.P) * a.M + row0 / a.P; }
+            gather4(dst + lane * grp_pitch, &map, 0, r[0], r[1], r[2], r[3], bar);
+        }
+    };
+    for (int i = 0; i < S && i < n_mine; ++i) issue(i);
+    long long tc[6] = {0, 0, 0, 0, 0, 0};
+    const int rows = U * W;
+    // row r = lane + 32u of every unit: byte offset of its position-feature slot and its env's feature increment
+    constexpr int kRounds = (U * 128 + 31) / 32;   // W <= 128
+    int off_u[kRounds]; float pfe_u[kRounds];
+#pragma unroll
+    for (int u = 0; u < kRounds; ++u) {
+        const int r = lane + 32 * u;
+        const int e = r / W, g = e >> 2;
+        off_u[u] = r < rows ? (int)(g * grp_pitch + (5 * (r - g * 4 * W) + 4) * 4) : -1;
+        pfe_u[u] = (float)e * 0.001f;
+    }
+    for (int i = 0; i < n_mine; ++i) {
+        const int s = i % S;
+        const int64_t env0 = (first + (int64_t)i * stride) * U;
+        long long t0 = clock64();
+        if (!mbar_wait_bounded(bars + 8 * s, (i / S) & 1)) { if (lane == 0) atomicAdd(a.err, 1); return; }
+        long long t1 = clock64(); tc[0] += t1 - t0;
+        unsigned char *o = ring + (size_t)s * pitch;
+        const float pf0 = (float)(uint32_t)env0 * 0.001f;
+#pragma unroll
+        for (int u = 0; u < kRounds; ++u)
+            if (off_u[u] >= 0) *reinterpret_cast<float *>(o + off_u[u]) = pf0 + pfe_u[u];
+        long long t2 = clock64(); tc[1] += t2 - t1;
+        fence_async();
+        __syncwarp();
+        long long t3 = clock64(); tc[2] += t3 - t2;
+        if (lane < G && !(a.flags & 1)) {
+            bulk_store(a.obs + ((size_t)env0 + 4 * lane) * W * 5, smem_u32(o) + lane * grp_pitch, grp_b);
+            bulk_commit();
+        }
+        long long t4 = clock64(); tc[3] += t4 - t3;
+        const int j = i - (a.lag - 1);
+        if (j >= 0 && j + S < n_mine) {
+            if (lane < G) { if (a.lag == 1) bulk_wait_read<0>(); else if (a.lag == 2) bulk_wait_read<1>(); else bulk_wait_read<2>(); }
+            __syncwarp();
+            long long t5 = clock64(); tc[4] += t5 - t4;
+            issue(j + S);
+            tc[5] += clock64() - t5;
+        }
+    }
+    if (lane < G) bulk_wait_read<0>();
+    if (blockIdx.x == 0 && threadIdx.x == 0) { for (int k = 0; k < 6; ++k) a.clk[k] = (unsigned long long)tc[k]; a.clk[6] = (unsigned long long)n_mine; }
+}
+
+__global__ void check_hash_kernel(const Args a, unsigned long long *bad) {
+    const int64_t n = a.N * a.W * 5;
+    const uint32_t span = (uint32_t)(a.T - a.W);
+    for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < n; f += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t env = f / (a.W * 5);
+        const int rem = (int)(f - env * a.W * 5), j = rem / 5, c = rem % 5;
+        const int64_t unit_envs = a.lag < 0 ? 1 : (int64_t)a.S;   // a.S carries the unit size for the check
+        const int64_t env0 = env / unit_envs * unit_envs;
+        const float want = c == 4 ? (float)(uint32_t)env0 * 0.001f + (float)(int)(env - env0) * 0.001f
+                                  : a.plain[((size_t)hash_row((uint32_t)env, span) + j) * 4 + c];
+        if (a.obs[f] != want) atomicAdd(bad, 1ull);
+    }
+}
+
 __global__ void check_kernel(const Args a, unsigned long long *bad) {
     const int64_t n = a.N * a.W * 5;
     for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < n; f += (int64_t)gridDim.x * blockDim.x) {
@@ -230,6 +527,103 @@ void run(const CUtensorMap &map, Args a, int sms, int nw, int S, int lag, int fl
     fflush(stdout);
 }
 
+
+template <typename L>
+void run_generic(const char *name, Args a, int sms, int flags, unsigned long long *bad_dev, L launch) {
+    a.flags = flags;
+    CHECK(cudaMemset(a.err, 0, sizeof(int)));
+    CHECK(cudaMemset(a.obs, 0xFF, (size_t)a.N * a.W * 20));
+    launch(a);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("%s flags %d: %s\n", name, flags, cudaGetErrorString(e)); exit(2); }
+    int err = 0;
+    CHECK(cudaMemcpy(&err, a.err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (err) { printf("%s flags %d: %d warps timed out\n", name, flags, err); return; }
+    unsigned long long bad = 0;
+    if (flags == 0) {
+        CHECK(cudaMemset(bad_dev, 0, 8));
+        check_kernel<<<sms * 8, 256>>>(a, bad_dev);
+        CHECK(cudaMemcpy(&bad, bad_dev, 8, cudaMemcpyDeviceToHost));
+    }
+    cudaEvent_t e0, e1;
+    CHECK(cudaEventCreate(&e0)); CHECK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) launch(a);
+    CHECK(cudaEventRecord(e0));
+    const int reps = 20;
+    for (int i = 0; i < reps; ++i) launch(a);
+    CHECK(cudaEventRecord(e1));
+    CHECK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    ms /= reps;
+    printf("%s  flags %d   %.4f ms   out %7.1f GB/s   mismatches %llu\n", name, flags, ms, (double)a.N * a.W * 20 / ms / 1e6, bad);
+    fflush(stdout);
+}
+
+template <int G>
+void run_a2(const CUtensorMap &map, Args a, int sms, int nw, int S, int lag, int flags, unsigned long long *bad_dev) {
+    const uint32_t pitch = G * ((4 * 20u * a.W + 127) & ~127u);
+    const size_t smem = (size_t)nw * (128 + (size_t)S * pitch);
+    if (smem > 226 * 1024) return;
+    a.S = S; a.lag = lag;
+    CHECK(cudaFuncSetAttribute(probe_a2_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    char name[128];
+    snprintf(name, sizeof name, "A2 unit %2d envs  warps %2d  S %d  lag %d  smem %6zu", 4 * G, nw, S, lag, smem);
+    run_generic(name, a, sms, flags, bad_dev, [&](const Args &aa) { probe_a2_kernel<G><<<sms, nw * 32, smem>>>(map, aa); });
+}
+
+void run_b(const CUtensorMap &map, Args a, int sms, int C, int S, int flags, unsigned long long *bad_dev) {
+    const size_t smem = 256 + 8 * 32 * 4 + (size_t)S * 8 * ((4 * 20u * a.W + 127) & ~127u);
+    if (smem > 226 * 1024 || S > 8) return;
+    a.S = S;
+    CHECK(cudaFuncSetAttribute(probe_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    char name[128];
+    snprintf(name, sizeof name, "B  tile 32 envs  consumers %d  S %d  smem %6zu", C, S, smem);
+    run_generic(name, a, sms, flags, bad_dev, [&](const Args &aa) { probe_b_kernel<<<sms, (C + 2) * 32, smem>>>(map, aa, C); });
+}
+
+template <int G>
+void run_a3(const CUtensorMap &map, Args a, int sms, int nw, int S, int lag, int flags, unsigned long long *bad_dev) {
+    const uint32_t pitch = G * ((4 * 20u * a.W + 127) & ~127u);
+    const size_t smem = (size_t)nw * (128 + (size_t)S * pitch);
+    if (smem > 226 * 1024) return;
+    a.S = S; a.lag = lag; a.flags = flags;
+    CHECK(cudaFuncSetAttribute(probe_a3_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CHECK(cudaMemset(a.err, 0, sizeof(int)));
+    CHECK(cudaMemset(a.obs, 0xFF, (size_t)a.N * a.W * 20));
+    auto launch = [&] { probe_a3_kernel<G><<<sms, nw * 32, smem>>>(map, a); };
+    launch();
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("A3 G %d nw %d: %s\n", G, nw, cudaGetErrorString(e)); exit(2); }
+    int err = 0;
+    CHECK(cudaMemcpy(&err, a.err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (err) { printf("A3 G %d nw %d S %d: %d warps timed out\n", G, nw, S, err); return; }
+    unsigned long long bad = 0;
+    if (flags == 0) {
+        CHECK(cudaMemset(bad_dev, 0, 8));
+        Args ac = a; ac.S = 4 * G;
+        check_hash_kernel<<<sms * 8, 256>>>(ac, bad_dev);
+        CHECK(cudaMemcpy(&bad, bad_dev, 8, cudaMemcpyDeviceToHost));
+    }
+    cudaEvent_t e0, e1;
+    CHECK(cudaEventCreate(&e0)); CHECK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) launch();
+    CHECK(cudaEventRecord(e0));
+    const int reps = 20;
+    for (int i = 0; i < reps; ++i) launch();
+    CHECK(cudaEventRecord(e1));
+    CHECK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    ms /= reps;
+    unsigned long long h[7];
+    CHECK(cudaMemcpy(h, a.clk, 56, cudaMemcpyDeviceToHost));
+    const double n = (double)h[6];
+    printf("A3 unit %2d envs  warps %2d  S %d  lag %d  flags %d  smem %6zu  %.4f ms  %7.1f GB/s  bad %llu | clk/unit: wait %5.0f pf %4.0f fence %4.0f store %4.0f wgroup %5.0f issue %5.0f\n",
+           4 * G, nw, S, lag, flags, smem, ms, (double)a.N * a.W * 20 / ms / 1e6, bad, h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[5] / n);
+    fflush(stdout);
+}
+
 int main(int argc, char **argv) {
     const int W = argc > 1 ? atoi(argv[1]) : 60;
     const int64_t N = argc > 2 ? atoll(argv[2]) : (1 << 20);
@@ -268,6 +662,7 @@ int main(int argc, char **argv) {
     CHECK(cudaMemcpy(d_inter, inter.data(), inter.size(), cudaMemcpyHostToDevice));
     CHECK(cudaMemcpy(d_row0, row0.data(), N * 4, cudaMemcpyHostToDevice));
     CHECK(cudaMemcpy(d_pf, pf.data(), N * 4, cudaMemcpyHostToDevice));
+    a.T = T; CHECK(cudaMalloc(&a.clk, 64));
     a.plain = d_plain; a.inter = d_inter; a.row0 = d_row0; a.pf = d_pf; a.obs = d_obs; a.N = N; a.W = W; a.M = (int)M; a.P = P; a.err = d_err;
 
     EncodeTiled encode = nullptr;
@@ -295,32 +690,22 @@ int main(int argc, char **argv) {
         if (r != CUDA_SUCCESS) return 1;
     }
 
-    // correctness + first timings
-    run<0>(map_inter, a, sms, 8, 4, 2, 0, d_bad);
-    run<1>(map_inter, a, sms, 8, 4, 2, 0, d_bad);
-    run<2>(map_plain, a, sms, 8, 4, 2, 0, d_bad);
-    run<3>(map_plain, a, sms, 8, 4, 2, 0, d_bad);
-    // sweeps
-    for (int nw : {4, 8, 12, 16, 24, 32})
-        for (int S : {2, 3, 4, 6})
-            for (int lag : {1, 2}) {
-                if (lag > S) continue;
-                run<0>(map_inter, a, sms, nw, S, lag, 0, d_bad);
-            }
-    for (int nw : {4, 8, 16, 32}) {
-        run<0>(map_inter, a, sms, nw, 3, 2, 1, d_bad); // loads only
-        run<0>(map_inter, a, sms, nw, 3, 2, 2, d_bad); // stores only
-        run<1>(map_inter, a, sms, nw, 3, 2, 0, d_bad);
-        run<1>(map_inter, a, sms, nw, 3, 2, 1, d_bad);
+    const bool v1 = argc > 4 && atoi(argv[4]) == 1;
+    if (v1) {
+        run<0>(map_inter, a, sms, 8, 4, 2, 0, d_bad);
+        run<1>(map_inter, a, sms, 8, 4, 2, 0, d_bad);
+        run<2>(map_plain, a, sms, 8, 4, 2, 0, d_bad);
+        run<3>(map_plain, a, sms, 8, 4, 2, 0, d_bad);
+        for (int nw : {8, 16}) { run<0>(map_inter, a, sms, nw, 2, 1, 0, d_bad); run<2>(map_plain, a, sms, nw, 2, 1, 0, d_bad); }
     }
-    for (int nw : {4, 8, 12, 16, 24})
-        for (int S : {2, 3, 4}) {
-            run<2>(map_plain, a, sms, nw, S, 1, 0, d_bad);
-        }
-    for (int nw : {8, 16}) {
-        run<2>(map_plain, a, sms, nw, 3, 1, 1, d_bad);
-        run<3>(map_plain, a, sms, nw, 3, 1, 0, d_bad);
-        run<3>(map_plain, a, sms, nw, 3, 1, 1, d_bad);
-    }
+    // v3: lanes < G issue their group's load and store; phase clocks
+    for (int nw : {8, 12, 16, 20, 24}) for (int S : {2, 3}) for (int lag : {1, 2}) run_a3<1>(map_inter, a, sms, nw, S, lag, 0, d_bad);
+    for (int nw : {6, 8, 10, 11}) for (int S : {2}) for (int lag : {1, 2}) run_a3<2>(map_inter, a, sms, nw, S, lag, 0, d_bad);
+    for (int nw : {4, 5, 7}) for (int S : {2, 3}) for (int lag : {1, 2}) run_a3<2>(map_inter, a, sms, nw, S, lag, 0, d_bad);
+    for (int nw : {3, 4, 5}) for (int S : {2}) for (int lag : {1, 2}) run_a3<4>(map_inter, a, sms, nw, S, lag, 0, d_bad);
+    for (int nw : {2}) for (int S : {2}) for (int lag : {1, 2}) run_a3<8>(map_inter, a, sms, nw, S, lag, 0, d_bad);
+    run_a3<1>(map_inter, a, sms, 16, 2, 1, 1, d_bad); run_a3<1>(map_inter, a, sms, 16, 2, 1, 2, d_bad);
+    run_a3<2>(map_inter, a, sms, 10, 2, 1, 1, d_bad); run_a3<2>(map_inter, a, sms, 10, 2, 1, 2, d_bad);
+    run_a3<4>(map_inter, a, sms, 5, 2, 1, 1, d_bad); run_a3<4>(map_inter, a, sms, 5, 2, 1, 2, d_bad);
     return 0;
 }
