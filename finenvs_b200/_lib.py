@@ -58,6 +58,7 @@ class FeState(C.Structure):
         ("terminated", C.c_void_p),
         ("ep_return", C.c_void_p),
         ("ep_len", C.c_void_p),
+        ("sched", C.c_void_p),
     ]
 
 
@@ -76,7 +77,7 @@ _PROTOTYPES = {
     "fe_error_string": (C.c_char_p, [C.c_int]),
     "fe_tile_envs": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
     "fe_pipe_envs": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
-    "fe_step_kernel_name": (C.c_char_p, [C.POINTER(FeParams), C.POINTER(FeSeries)]),
+    "fe_step_kernel_name": (C.c_char_p, [C.POINTER(FeParams), C.POINTER(FeSeries), C.POINTER(FeState)]),
     "fe_obs_table_bytes": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
     "fe_obs_table_build": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "fe_log_returns": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),

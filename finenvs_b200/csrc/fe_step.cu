@@ -111,29 +111,60 @@ __device__ __forceinline__ EnvResult env_observe(const FeParams &p, const FeSeri
     return r;
 }
 
+// The loads of one env-step, split from the arithmetic so that a caller can issue them ahead of time (the gather
+// variant's bookkeeper warps keep the loads of the next two tiles in flight while they compute the current one: under a
+// saturated write stream a dependent HBM load costs several thousand cycles, and the chain state -> segment table ->
+// price row was what bounded the persistent kernels' bookkeeping at ~0.16 ms per 1 Mi envs).
+struct EnvLoads {   // per-env state + action (first hop)
+    int32_t seg, ptr;
+    float cash, lng, sht, act;
+    double margin;
+};
+struct EnvBar {     // current bar of the env (second / third hop: needs seg and ptr)
+    int32_t len;
+    int64_t row0;   // first row of the window AFTER the time pointer advanced
+    double O, H, L, C;
+};
+__device__ __forceinline__ EnvLoads env_load_state(const FeState &st, const float *__restrict__ actions, int64_t i) {
+    EnvLoads e;
+    e.act = __ldg(actions + i);
+    e.seg = st.seg[i];
+    e.ptr = st.ptr[i];
+    e.cash = st.cash[i];
+    e.lng = st.long_sh[i];
+    e.sht = st.short_sh[i];
+    e.margin = st.margin[i];
+    return e;
+}
+__device__ __forceinline__ EnvBar env_load_bar(const FeParams &p, const FeSeries &s, const EnvLoads &e) {
+    EnvBar b;
+    b.len = __ldg(s.seg_len + e.seg);
+    b.row0 = __ldg(s.seg_start + e.seg) + e.ptr + 1; // :281-282 advance time
+    // :323-342 current bar = last row of the window: O,H,L,C as two 16-byte loads
+    const double2 *px = reinterpret_cast<const double2 *>(s.prices + (b.row0 + p.window - 1) * 4);
+    const double2 oh = __ldg(px), lc = __ldg(px + 1);
+    b.O = oh.x; b.H = oh.y; b.L = lc.x; b.C = lc.y;
+    return b;
+}
+
 template <typename OutT>
-__device__ __forceinline__ EnvResult env_step(const FeParams &p, const FeSeries &s, const FeState &st,
-                                              const Consts &k, int64_t i, const float *__restrict__ actions,
-                                              OutT *__restrict__ rewards, int32_t *__restrict__ dones,
-                                              bool track, uint64_t step) {
+__device__ __forceinline__ EnvResult env_compute(const FeParams &p, const FeSeries &s, const FeState &st, const Consts &k,
+                                                 int64_t i, const EnvLoads &ld, const EnvBar &bar, OutT *__restrict__ rewards,
+                                                 int32_t *__restrict__ dones, bool track, uint64_t step) {
     EnvResult res;
     const int W = p.window;
     // :298-302 action -> integer share delta (round half to even, then clamp)
-    float d = rintf(fmul(__ldg(actions + i), k.scale));
+    float d = rintf(fmul(ld.act, k.scale));
     d = d < -k.ms ? -k.ms : (d > k.ms ? k.ms : d);
-    // :281-282 advance time
-    int32_t seg = st.seg[i];
-    int32_t ptr = st.ptr[i] + 1;
-    const int32_t len = __ldg(s.seg_len + seg);
-    res.row0 = __ldg(s.seg_start + seg) + ptr;
-    // :323-342 current bar = last row of the window: O,H,L,C as two 16-byte loads
-    const double2 *px = reinterpret_cast<const double2 *>(s.prices + (res.row0 + W - 1) * 4);
-    const double2 oh = __ldg(px), lc = __ldg(px + 1);
-    const double O = oh.x, H = oh.y, L = lc.x, C = lc.y;
-    float cash = st.cash[i];
-    float lng = st.long_sh[i];
-    float sht = st.short_sh[i];
-    double margin = st.margin[i];
+    int32_t seg = ld.seg;
+    int32_t ptr = ld.ptr + 1;
+    const int32_t len = bar.len;
+    res.row0 = bar.row0;
+    const double O = bar.O, H = bar.H, L = bar.L, C = bar.C;
+    float cash = ld.cash;
+    float lng = ld.lng;
+    float sht = ld.sht;
+    double margin = ld.margin;
     float comm = 0.0f; // :305
     // :344-351
     float pos = d < 0.0f ? 0.0f : d;
@@ -236,6 +267,16 @@ __device__ __forceinline__ EnvResult env_step(const FeParams &p, const FeSeries 
     if (k.rewards_mirror) reinterpret_cast<OutT *>(k.rewards_mirror)[i] = (OutT)rew;
     if (k.dones_mirror) k.dones_mirror[i] = done;
     return res;
+}
+
+template <typename OutT>
+__device__ __forceinline__ EnvResult env_step(const FeParams &p, const FeSeries &s, const FeState &st,
+                                              const Consts &k, int64_t i, const float *__restrict__ actions,
+                                              OutT *__restrict__ rewards, int32_t *__restrict__ dones,
+                                              bool track, uint64_t step) {
+    const EnvLoads ld = env_load_state(st, actions, i);
+    const EnvBar bar = env_load_bar(p, s, ld);
+    return env_compute<OutT>(p, s, st, k, i, ld, bar, rewards, dones, track, step);
 }
 
 // one atomic per warp for the episode statistics
@@ -613,19 +654,23 @@ fe_pipe_kernel(const FeParams p, const FeSeries s, const FeState st, const Const
 //                               and issues the gather of unit i + S into it.
 // ------------------------------------------------------------------------------------------
 #ifndef FE_GATHER_BOOK
-#define FE_GATHER_BOOK 6
+#define FE_GATHER_BOOK 8
 #endif
 #ifndef FE_GATHER_MOVE
 #define FE_GATHER_MOVE 12
 #endif
+#ifndef FE_GATHER_STAGES
+#define FE_GATHER_STAGES 3 /* slots per mover when they fit (else 2) */
+#endif
 constexpr int kGaBook = FE_GATHER_BOOK;
 constexpr int kGaMove = FE_GATHER_MOVE;
 constexpr int kGaThreads = (kGaBook + kGaMove) * 32;
-constexpr int kGaQ = 16;          // descriptor ring depth in tiles (movers keep a descriptor until its unit is stored)
+constexpr int kGaQ = 32;          // descriptor ring depth in tiles (movers keep a descriptor until its unit is stored)
 constexpr int kGaMaxStages = 4;
-constexpr int kGaBarBytes = 1024; // desc_full[Q], desc_free[Q], full[kGaMove][kGaMaxStages]
+constexpr int kGaBarBytes = 1280; // desc_full[Q], desc_free[Q], full[kGaMove][kGaMaxStages]; last 16 bytes: claim lock + sequence
 constexpr int kGaPitch = 80;      // tensor row pitch of the observation-layout table: P * row bytes for both dtypes
 
+static_assert((2 * kGaQ + kGaMove * kGaMaxStages) * 8 + 16 <= kGaBarBytes, "mbarrier area too small");
 __host__ __device__ inline int ga_row_bytes(bool f64) { return f64 ? 40 : 20; }
 __host__ __device__ inline int ga_phase_shift(bool f64) { return f64 ? 1 : 2; } // log2 P, P = 16 / gcd(16, row bytes)
 // tensor rows per shifted copy: enough for every window start, plus slack so that the last windows stay inside the copy
@@ -642,8 +687,11 @@ __host__ __device__ inline bool ga_window_ok(int W, bool f64) {
     return (inner % 16) == 0 && inner <= 2048;
 }
 __host__ __device__ inline uint32_t ga_slot_pitch(int W, bool f64) { return (4u * ga_row_bytes(f64) * W + 127u) & ~127u; }
+template <typename OutT> __host__ __device__ inline size_t gather_desc_bytes() { // tile id + 32 x {row index, feature} per slot
+    return ((size_t)kGaQ * (4 + 32 * (4 + sizeof(OutT))) + 127) & ~(size_t)127;
+}
 template <typename OutT> __host__ __device__ inline size_t gather_smem_bytes(int W, int S) {
-    return kGaBarBytes + (size_t)kGaQ * 32 * (4 + sizeof(OutT)) + (size_t)kGaMove * S * ga_slot_pitch(W, sizeof(OutT) == 8);
+    return kGaBarBytes + gather_desc_bytes<OutT>() + (size_t)kGaMove * S * ga_slot_pitch(W, sizeof(OutT) == 8);
 }
 
 __device__ __forceinline__ void tma_gather4(uint32_t dst_smem, const CUtensorMap *map, int r0, int r1, int r2, int r3, uint32_t bar) {
@@ -653,119 +701,246 @@ __device__ __forceinline__ void tma_gather4(uint32_t dst_smem, const CUtensorMap
         : "memory");
 }
 
+#ifdef FE_GATHER_CLOCKS
+// experiment builds: cycles spent per phase by block 0's mover 0 / bookkeeper 0 (tools/gather_clocks.py)
+__device__ unsigned long long fe_gather_clk[16];
+__device__ unsigned long long fe_gather_block_ns[3 * 160]; // per block: start, all movers done, smid (globaltimer ns)
+__device__ __forceinline__ unsigned long long ga_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define GA_CLK(var) const long long var = clock64()
+#define GA_ACC(slot, a, b) acc[slot] += (b) - (a)
+#else
+#define GA_CLK(var)
+#define GA_ACC(slot, a, b)
+#endif
+
 template <typename OutT, bool kObserve>
 __global__ void __launch_bounds__(kGaThreads, 1)
 fe_gather_kernel(const __grid_constant__ CUtensorMap tmap, const FeParams p, const FeSeries s, const FeState st, const Consts k,
                  const float *__restrict__ actions, OutT *__restrict__ obs, OutT *__restrict__ rewards,
                  int32_t *__restrict__ dones, FeStats *stats, const uint64_t step_arg, const uint64_t *__restrict__ step_dev,
-                 const int S, const int rows_per_phase) {
+                 const int S, const int rows_per_phase, unsigned int *__restrict__ sched) {
     constexpr bool kF64 = sizeof(OutT) == 8;
     extern __shared__ __align__(128) unsigned char smem[];
     const uint64_t step = step_dev ? *step_dev : step_arg;
     const int W = p.window;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t ntiles_all = (p.num_envs + 31) / 32;
-    const int ntiles = (int)((ntiles_all - blockIdx.x + gridDim.x - 1) / gridDim.x); // tiles blockIdx.x, +gridDim.x, ...
+    const int ntiles_all = (int)((p.num_envs + 31) / 32);
     const uint32_t bars = smem_u32(smem);
     auto desc_full = [&](int q) { return bars + 8u * q; };
     auto desc_free = [&](int q) { return bars + 8u * (kGaQ + q); };
     auto slot_full = [&](int m, int si) { return bars + 8u * (2 * kGaQ + m * kGaMaxStages + si); };
-    int32_t *d_row = reinterpret_cast<int32_t *>(smem + kGaBarBytes);                          // [Q][32] tensor row index
-    OutT *d_pf = reinterpret_cast<OutT *>(smem + kGaBarBytes + (size_t)kGaQ * 32 * 4);         // [Q][32]
-    unsigned char *ring = smem + kGaBarBytes + (size_t)kGaQ * 32 * (4 + sizeof(OutT));
+    unsigned int *claim = reinterpret_cast<unsigned int *>(smem + kGaBarBytes - 16);         // [0] lock, [1] next sequence number
+    int32_t *d_tile = reinterpret_cast<int32_t *>(smem + kGaBarBytes);                         // [Q] tile id, -1 = no more tiles
+    int32_t *d_row = d_tile + kGaQ;                                                            // [Q][32] tensor row index
+    OutT *d_pf = reinterpret_cast<OutT *>(smem + kGaBarBytes + (size_t)kGaQ * (4 + 32 * 4));   // [Q][32]
+    unsigned char *ring = smem + kGaBarBytes + gather_desc_bytes<OutT>();
     const uint32_t pitch = ga_slot_pitch(W, kF64);
-    auto tile_env0 = [&](int t) { return ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * 32; };
 
+#ifdef FE_GATHER_CLOCKS
+    if (tid == 0 && blockIdx.x < 160) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        fe_gather_block_ns[3 * blockIdx.x] = ga_globaltimer();
+        fe_gather_block_ns[3 * blockIdx.x + 2] = smid;
+        fe_gather_block_ns[3 * blockIdx.x + 1] = 0;
+    }
+#endif
     if (tid == 0) {
         for (int q = 0; q < kGaQ; ++q) { mbar_init(desc_full(q), 1); mbar_init(desc_free(q), 8); }
         for (int m = 0; m < kGaMove; ++m)
             for (int si = 0; si < kGaMaxStages; ++si) mbar_init(slot_full(m, si), 1);
+        claim[0] = 0; claim[1] = 0;
         mbar_fence_init();
     }
     __syncthreads();
 
     if (warp < kGaBook) {
         // ------------------------------------------------------------------ bookkeepers
+        // Tiles are CLAIMED, not pre-assigned: SMs differ by ~15 % in how fast they move this traffic (position relative
+        // to the L2 slices / the two dies), and with a static round-robin the slowest SM set the kernel time (232 ... 273 us
+        // per block, profiles/r02_gather_clocks.txt).  A claim = (next sequence number of this block, next tile of the
+        // grid), taken together under a block-local lock so that sequence order = tile order: once a sequence slot says
+        // "no more tiles", every later one does.
         const int shift = ga_phase_shift(kF64);
-        for (int t = warp; t < ntiles; t += kGaBook) {
-            const int q = t % kGaQ;
-            mbar_wait(desc_free(q), ((t / kGaQ) & 1) ^ 1); // first lap passes immediately
-            const int64_t env0 = tile_env0(t);
-            const int nvalid = (int)min((int64_t)32, p.num_envs - env0);
+#ifdef FE_GATHER_CLOCKS
+        long long acc[16] = {0};
+        int ntl = 0;
+#endif
+        for (;;) {
+            int n = 0, t = 0; // sequence slot of this block, tile of the grid (>= ntiles_all: none left)
+            if (lane == 0) {
+                while (atomicCAS(&claim[0], 0u, 1u) != 0u) {}
+                n = (int)claim[1];
+                claim[1] = (unsigned)n + 1;
+                t = (int)atomicAdd(&sched[0], 1u);
+                __threadfence_block();
+                atomicExch(&claim[0], 0u);
+            }
+            n = __shfl_sync(0xFFFFFFFFu, n, 0);
+            t = __shfl_sync(0xFFFFFFFFu, t, 0);
+            const int q = n & (kGaQ - 1);
+            GA_CLK(c0);
+            if (lane == 0) mbar_wait(desc_free(q), ((n / kGaQ) & 1) ^ 1); // first lap passes immediately
+            __syncwarp();
+            GA_CLK(c1);
+            GA_ACC(8, c0, c1);
+            if (t >= ntiles_all) { // nothing left: tell the movers and stop
+                if (lane == 0) { d_tile[q] = -1; mbar_arrive(desc_full(q)); }
+                break;
+            }
+            const int64_t i = (int64_t)t * 32 + lane;
+            const bool active = i < p.num_envs;
             EnvResult r;
             r.done = 0; r.newly_terminated = 0; r.fin_return = 0.0; r.fin_len = 0; r.row0 = 0; r.posfeat = 0.0;
-            const bool active = lane < nvalid;
             if (active) {
-                const int64_t i = env0 + lane;
                 if (kObserve) r = env_observe(p, s, st, k, i);
                 else r = env_step<OutT>(p, s, st, k, i, actions, rewards, dones, stats != nullptr, step);
             }
             // window starting at series row row0 = copy (row0 mod P), tensor row (row0 div P) of that copy
             d_row[q * 32 + lane] = (int32_t)((r.row0 & ((1 << shift) - 1)) * rows_per_phase + (r.row0 >> shift));
             d_pf[q * 32 + lane] = (OutT)r.posfeat;
+            if (lane == 0) d_tile[q] = t;
             if (!kObserve) accumulate_stats(stats, r, active);
             __syncwarp();
             if (lane == 0) mbar_arrive(desc_full(q)); // release: descriptor visible to the movers
+            GA_CLK(c2);
+            GA_ACC(9, c1, c2);
+#ifdef FE_GATHER_CLOCKS
+            ++ntl;
+#endif
         }
+#ifdef FE_GATHER_CLOCKS
+        if (blockIdx.x == 0 && tid == 0) { fe_gather_clk[8] = acc[8]; fe_gather_clk[9] = acc[9]; fe_gather_clk[10] = ntl; }
+#endif
     } else {
         // ------------------------------------------------------------------ movers
+#ifdef FE_GATHER_CLOCKS
+        long long acc[16] = {0};
+        const long long mover_t0 = clock64();
+#endif
         const int m = warp - kGaBook;
         const uint32_t row_b = (uint32_t)ga_row_bytes(kF64) * W, unit_b = 4 * row_b;
-        int nunits = 0; // units of this block: 8 per tile, fewer in a ragged last tile
-        if (ntiles > 0) {
-            const int last = (int)min((int64_t)32, p.num_envs - tile_env0(ntiles - 1));
-            nunits = (ntiles - 1) * 8 + (last + 3) / 4;
-        }
-        const int n_mine = m < nunits ? (nunits - m + kGaMove - 1) / kGaMove : 0;
         unsigned char *slots = ring + (size_t)m * S * pitch;
-        // rows lane, lane + 32, ... of a unit (4W rows, dense): which of the unit's 4 envs each belongs to, 2 bits per round
-        constexpr int kRounds = kF64 ? 7 : 13; // ceil(4W / 32) for the largest W ga_window_ok() admits
-        uint32_t env_of_round = 0;
+        // position-feature column: env e of a unit owns rows [eW, (e+1)W) of the slot; this lane writes rows eW + lane + 32k
+        constexpr int kRounds = kF64 ? 2 : 4; // ceil(W / 32) for the largest W ga_window_ok() admits (51 / 102)
+        uint32_t round_mask = 0;              // bit k: lane + 32k < W
 #pragma unroll
-        for (int u = 0; u < kRounds; ++u) {
-            const int r = lane + 32 * u;
-            env_of_round |= (uint32_t)min(r / W, 3) << (2 * u);
-        }
-        const int rounds = (4 * W + 31) / 32;
-        auto issue = [&](int i) { // lane 0: gather of this mover's unit i into slot i % S
-            const int u = m + i * kGaMove, t = u >> 3, g = u & 7, q = t % kGaQ, si = i % S;
-            mbar_wait(desc_full(q), (t / kGaQ) & 1);
+        for (int kk = 0; kk < kRounds; ++kk) round_mask |= (uint32_t)(lane + 32 * kk < W) << kk;
+        const uint32_t env_stride = (uint32_t)W * 5; // values per env
+        // unit i of this mover = group (m + i * kGaMove) % 8 of the block's sequence slot (m + i * kGaMove) / 8
+        static_assert((kGaQ & (kGaQ - 1)) == 0, "kGaQ must be a power of two");
+        int iss_u = m, iss_si = 0; // lane 0: next unit to issue (unit number within the block, slot)
+        int issued = 0;            // lane 0: units whose gather has been issued
+        bool open = true;          // lane 0: more units may follow (no "no more tiles" slot seen yet)
+        auto issue = [&]() {       // lane 0: gather of the next unit into slot iss_si
+            const int n = iss_u >> 3, g = iss_u & 7, q = n & (kGaQ - 1);
+            GA_CLK(c0);
+            mbar_wait(desc_full(q), (n / kGaQ) & 1);
+            GA_CLK(c1);
+            GA_ACC(4, c0, c1);
+            if (d_tile[q] < 0) { open = false; return; }
             const int4 rows4 = *reinterpret_cast<const int4 *>(d_row + q * 32 + 4 * g);
-            mbar_arrive_expect_tx(slot_full(m, si), unit_b);
-            tma_gather4(smem_u32(slots + (size_t)si * pitch), &tmap, rows4.x, rows4.y, rows4.z, rows4.w, slot_full(m, si));
+#ifdef FE_GATHER_NOLOAD
+            if (rows4.x == -12345)
+#endif
+            {
+                mbar_arrive_expect_tx(slot_full(m, iss_si), unit_b);
+                tma_gather4(smem_u32(slots + (size_t)iss_si * pitch), &tmap, rows4.x, rows4.y, rows4.z, rows4.w, slot_full(m, iss_si));
+            }
+#ifdef FE_GATHER_NOLOAD
+            mbar_arrive(slot_full(m, iss_si));
+#endif
+            ++issued;
+            iss_u += kGaMove;
+            iss_si = iss_si + 1 == S ? 0 : iss_si + 1;
+            GA_CLK(c2);
+            GA_ACC(5, c1, c2);
         };
         if (lane == 0)
-            for (int i = 0; i < S && i < n_mine; ++i) issue(i);
-        for (int i = 0; i < n_mine; ++i) {
-            const int u = m + i * kGaMove, t = u >> 3, g = u & 7, q = t % kGaQ, si = i % S;
-            const int64_t env0 = tile_env0(t) + 4 * g;
-            const int nv = (int)min((int64_t)4, p.num_envs - env0);
-            mbar_wait(slot_full(m, si), (i / S) & 1); // the four windows have landed; desc_full(q) completed long ago
+            for (int i = 0; i < S && open; ++i) issue();
+        // Per unit: lane 0 waits until the gather has landed (one lane, then __syncwarp: a try_wait run by all 32 lanes on a
+        // per-thread address is serialised lane by lane, ~30 cycles each) -> the warp writes the 4W position features ->
+        // proxy fence -> lane 0 issues the bulk store, hands the descriptor entries back, waits until the store has read
+        // the slot and issues the next gather into it.
+        int u = m, si = 0;
+        uint32_t slot_phase = 0; // bit si: parity the mover waits for on slot_full(m, si)
+        int n_iss = __shfl_sync(0xFFFFFFFFu, issued, 0);
+        for (int i = 0; i < n_iss; ++i) {
+            const int n = u >> 3, g = u & 7, q = n & (kGaQ - 1);
+            GA_CLK(c0);
+            if (lane == 0) mbar_wait(slot_full(m, si), (slot_phase >> si) & 1u); // the four windows have landed
+            __syncwarp();
+            GA_CLK(c1);
+            GA_ACC(0, c0, c1);
             unsigned char *slot = slots + (size_t)si * pitch;
             const OutT *pf = d_pf + q * 32 + 4 * g;
-            const OutT pf0 = pf[0], pf1 = pf[1], pf2 = pf[2], pf3 = pf[3];
-            OutT *col = reinterpret_cast<OutT *>(slot) + 5 * lane + 4; // position-feature slot of row `lane`
+            OutT *col = reinterpret_cast<OutT *>(slot) + 5 * lane + 4; // position-feature slot of row `lane` of env 0
+#ifdef FE_GATHER_NOPF
+            if (pf[0] == (OutT)12345.678)
+#endif
 #pragma unroll
-            for (int uu = 0; uu < kRounds; ++uu) {
-                if (uu < rounds && lane + 32 * uu < 4 * W) {
-                    const uint32_t e = (env_of_round >> (2 * uu)) & 3u;
-                    col[160 * uu] = e == 0 ? pf0 : e == 1 ? pf1 : e == 2 ? pf2 : pf3;
-                }
+            for (int e = 0; e < 4; ++e) {
+                const OutT v = pf[e];
+#pragma unroll
+                for (int kk = 0; kk < kRounds; ++kk)
+                    if (round_mask & (1u << kk)) col[e * env_stride + 160 * kk] = v;
             }
+            GA_CLK(c1b);
+            GA_ACC(1, c1, c1b);
+#ifndef FE_GATHER_NOFENCE
             fence_proxy_async_smem(); // generic-proxy writes -> visible to the bulk store
+#endif
             __syncwarp();
+            GA_CLK(c2);
+            GA_ACC(11, c1b, c2);
             if (lane == 0) {
-                bulk_store(obs + (size_t)env0 * W * 5, smem_u32(slot), (uint32_t)nv * row_b);
-                bulk_commit();
+                const int64_t env0 = (int64_t)d_tile[q] * 32 + 4 * g;
+                const int64_t left = p.num_envs - env0;
+                const int nv = left >= 4 ? 4 : (left > 0 ? (int)left : 0); // < 4 only in the ragged last tile
+#ifdef FE_GATHER_NOSTORE
+                if (nv > 4)
+#else
+                if (nv > 0)
+#endif
+                {
+                    bulk_store(obs + (size_t)env0 * W * 5, smem_u32(slot), (uint32_t)nv * row_b);
+                    bulk_commit();
+                }
                 mbar_arrive(desc_free(q)); // this unit's descriptor entries are consumed
-                if (i + S < n_mine) {
+                GA_CLK(c3);
+                GA_ACC(2, c2, c3);
+                if (open) {
                     bulk_wait_read_all(); // the store has read the slot: refill it
-                    issue(i + S);
+                    GA_CLK(c4);
+                    GA_ACC(3, c3, c4);
+                    issue();
                 }
             }
             __syncwarp();
+            n_iss = __shfl_sync(0xFFFFFFFFu, issued, 0); // every issued unit gets stored; none follows once the stream closed
+            slot_phase ^= 1u << si;
+            u += kGaMove;
+            si = si + 1 == S ? 0 : si + 1;
         }
         if (lane == 0) bulk_wait_read_all();
+#ifdef FE_GATHER_CLOCKS
+        if (lane == 0 && blockIdx.x < 160) atomicMax(&fe_gather_block_ns[3 * blockIdx.x + 1], ga_globaltimer());
+        if (blockIdx.x == 0 && m == 0 && lane == 0) { for (int c = 0; c < 6; ++c) fe_gather_clk[c] = acc[c]; fe_gather_clk[6] = issued; fe_gather_clk[11] = acc[11]; fe_gather_clk[12] = 0; fe_gather_clk[13] = clock64() - mover_t0; }
+#endif
+    }
+    // the last block out rewinds the tile counter for the next launch (every block's claims precede its arrival here)
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(&sched[1], 1u) == gridDim.x - 1) {
+            sched[0] = 0;
+            sched[1] = 0;
+            __threadfence();
+        }
     }
 }
 
@@ -1355,6 +1530,7 @@ int check_common(const FeParams *p, const FeSeries *s, const FeState *st) {
     if (!st->seg || !st->ptr || !st->cash || !st->long_sh || !st->short_sh || !st->margin) return FE_EINVAL;
     if (p->evaluate && (!st->terminated || !st->ep_return)) return FE_EINVAL;
     if (((uintptr_t)s->prices | (uintptr_t)s->logret | (uintptr_t)s->obs_table) & 15) return FE_EALIGN;
+    if ((uintptr_t)st->sched & 7) return FE_EALIGN;
     return 0;
 }
 
@@ -1398,7 +1574,7 @@ int pick_pipe_stages(const FeParams &p, bool f64) {
 // slots per mover of the gather variant (3 when they fit, else 2); 0 = this window has no gather variant
 int pick_gather_stages(int W, bool f64) {
     if (!ga_window_ok(W, f64)) return 0;
-    for (int S = 3; S >= 2; --S)
+    for (int S = FE_GATHER_STAGES; S >= 2; --S)
         if ((f64 ? gather_smem_bytes<double>(W, S) : gather_smem_bytes<float>(W, S)) <= (size_t)kSmemMax) return S;
     return 0;
 }
@@ -1433,7 +1609,7 @@ struct StepChoice {
     int S;       // gather: slots per mover
     int threads; // tile: threads per block
 };
-StepChoice choose_kernel(const FeParams &p, const FeSeries &s, bool f64, int sms) {
+StepChoice choose_kernel(const FeParams &p, bool gather_ready, bool f64, int sms) {
     StepChoice c = {K_DIRECT, 0, 0, 0, kThreads};
     if (p.num_assets > 1 || p.variant == FE_VARIANT_PORTFOLIO) { c.kern = K_PORTFOLIO; return c; }
     if (p.variant == FE_VARIANT_SPLIT) { c.kern = K_SPLIT; return c; }
@@ -1442,11 +1618,11 @@ StepChoice choose_kernel(const FeParams &p, const FeSeries &s, bool f64, int sms
     if (p.variant == FE_VARIANT_GATHER || p.variant == FE_VARIANT_AUTO) {
         c.S = pick_gather_stages(p.window, f64);
         if (p.variant == FE_VARIANT_GATHER) {
-            c.kern = !s.obs_table ? K_ERR_TABLE : c.S == 0 ? K_ERR_SMEM : K_GATHER;
+            c.kern = !gather_ready ? K_ERR_TABLE : c.S == 0 ? K_ERR_SMEM : K_GATHER;
             return c;
         }
         const bool no_gather = env_override("FE_NO_GATHER") != 0; // sweeps: "auto" never picks gather
-        if (!no_gather && s.obs_table && c.S > 0 && worth_persistent && p.window >= 24 && gather_table_resident(p, f64)) {
+        if (!no_gather && gather_ready && c.S > 0 && worth_persistent && p.window >= 24 && gather_table_resident(p, f64)) {
             c.kern = K_GATHER;
             return c;
         }
@@ -1537,7 +1713,7 @@ int launch(const FeParams &p, const FeSeries &s, const FeState &st, const float 
     int sms = 0;
     int rc = device_sm_count(p.device, &sms);
     if (rc) return rc;
-    const StepChoice c = choose_kernel(p, s, sizeof(OutT) == 8, sms);
+    const StepChoice c = choose_kernel(p, s.obs_table && st.sched, sizeof(OutT) == 8, sms);
     switch (c.kern) {
     case K_ERR_SMEM: return FE_ESMEM;
     case K_ERR_TABLE: return FE_EINVAL;
@@ -1583,7 +1759,7 @@ int launch(const FeParams &p, const FeSeries &s, const FeState &st, const float 
         const int64_t ntiles = (p.num_envs + 31) / 32;
         const unsigned blocks = (unsigned)(ntiles < sms ? ntiles : sms);
         kern<<<blocks, kGaThreads, gather_smem_bytes<OutT>(p.window, c.S), stream>>>(
-            tmap, p, s, st, k, actions, (OutT *)obs, (OutT *)rewards, dones, stats, step, step_dev, c.S, (int)rpp);
+            tmap, p, s, st, k, actions, (OutT *)obs, (OutT *)rewards, dones, stats, step, step_dev, c.S, (int)rpp, st.sched);
         break;
     }
     case K_PIPE: {
@@ -1667,7 +1843,7 @@ int fe_version(void) { return FE_ABI_VERSION; }
 const char *fe_error_string(int code) {
     switch (code) {
     case 0: return "ok";
-    case FE_EINVAL: return "finenvs_b200: invalid argument (null pointer, non-positive size, num_assets outside 1..32, or the gather variant without FeSeries.obs_table)";
+    case FE_EINVAL: return "finenvs_b200: invalid argument (null pointer, non-positive size, num_assets outside 1..32, or the gather variant without FeSeries.obs_table / FeState.sched)";
     case FE_EALIGN: return "finenvs_b200: pointer not 16-byte aligned";
     case FE_ESMEM: return "finenvs_b200: window does not fit the requested kernel variant";
     case FE_EIO: return "finenvs_b200: cannot open or map the file";
@@ -1686,13 +1862,12 @@ int fe_pipe_envs(int32_t window, int32_t out_f64, int32_t stream_flavour) {
     return window > 0 ? pick_pipe_envs(window, out_f64 != 0, stream_flavour ? kPipeSInStream : 0) : 0;
 }
 
-const char *fe_step_kernel_name(const FeParams *p, const FeSeries *s) {
+const char *fe_step_kernel_name(const FeParams *p, const FeSeries *s, const FeState *st) {
     if (!p) return "";
     const bool f64 = p->out_f64 != 0;
     int sms = 148;
     (void)device_sm_count(p->device, &sms);
-    const FeSeries none = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    const StepChoice c = choose_kernel(*p, s ? *s : none, f64, sms);
+    const StepChoice c = choose_kernel(*p, s && s->obs_table && st && st->sched, f64, sms);
     switch (c.kern) {
     case K_PORTFOLIO:
         return f64 ? "fe_portfolio_book_kernel + fe_portfolio_stream_kernel<double>" : "fe_portfolio_book_kernel + fe_portfolio_stream_kernel<float>";
@@ -1703,7 +1878,7 @@ const char *fe_step_kernel_name(const FeParams *p, const FeSeries *s) {
                           : (f64 ? "fe_pipe_kernel<double,stream>" : "fe_pipe_kernel<float,stream>");
     case K_TILE: return f64 ? "fe_tile_kernel<double>" : "fe_tile_kernel<float>";
     case K_DIRECT: return f64 ? "fe_direct_kernel<double>" : "fe_direct_kernel<float>";
-    case K_ERR_TABLE: return "none (the gather variant needs FeSeries.obs_table)";
+    case K_ERR_TABLE: return "none (the gather variant needs FeSeries.obs_table and FeState.sched)";
     default: return "none (window does not fit the requested variant)";
     }
 }
@@ -1889,7 +2064,7 @@ static int step_host_impl(const FeParams *p, const FeSeries *s, const FeState *s
         // sit on its shared memory while it waits for its actions and write 16-byte PCIe packets (measured W = 60,
         // 1 Mi envs: 1.04 ms zero-copy, 0.77 ms with a copy-engine upload + zero-copy writes, vs 0.36 ms
         // device-resident): those take the chunked copy pipeline below.
-        const StepKernel kk = choose_kernel(*p, *s, p->out_f64 != 0, sms).kern;
+        const StepKernel kk = choose_kernel(*p, s->obs_table && st->sched, p->out_f64 != 0, sms).kern;
         if (ok && kk != K_TILE && kk != K_DIRECT) {
             const float *a = (const float *)aa.devicePointer;
             int32_t *dmirror = dones_host ? (int32_t *)ad.devicePointer : nullptr;
@@ -1928,7 +2103,9 @@ static int step_host_impl(const FeParams *p, const FeSeries *s, const FeState *s
         FeParams pc = *p;
         pc.num_envs = cnt;
         pc.env_id_base = p->env_id_base + off;
+        if (pc.variant == FE_VARIANT_GATHER) pc.variant = FE_VARIANT_AUTO;
         FeState sc = *st;
+        sc.sched = nullptr; // the chunks run concurrently on side streams: they cannot share the gather kernel's tile counter
         sc.seg += off; sc.ptr += off; sc.cash += off;
         sc.long_sh += off * A; sc.short_sh += off * A; sc.margin += off * A;
         if (sc.terminated) sc.terminated += off;
@@ -1990,6 +2167,11 @@ int fe_reset_all(const FeParams *p, const FeSeries *s, const FeState *st, uint64
                                                                                                  redraw);
     return (int)cudaGetLastError();
 }
+
+#ifdef FE_GATHER_CLOCKS
+int fe_debug_gather_clocks(unsigned long long out[16]) { return (int)cudaMemcpyFromSymbol(out, fe_gather_clk, 128); }
+int fe_debug_gather_blocks(unsigned long long out[480]) { return (int)cudaMemcpyFromSymbol(out, fe_gather_block_ns, 480 * 8); }
+#endif
 
 void fe_philox(uint64_t seed, uint64_t env_id, uint64_t step, uint32_t kind, uint32_t out[4]) {
     philox4x32_10(seed, env_id, step, kind, out);

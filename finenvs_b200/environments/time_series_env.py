@@ -293,6 +293,7 @@ class TimeSeriesEnv(BaseObject):
             int(self.random_offset), int(self.evaluate), int(self.obs_dtype == torch.float64), variant,
             dev.index if dev.index is not None else torch.cuda.current_device(),
         )
+        self._sched = torch.zeros(2, dtype=torch.int32, device=dev)   # gather kernel: tile counter (FeState.sched)
         s = self.series
         # the observation-layout table is only built for envs that can use it (large populations or variant="gather")
         want_table = variant == _lib.VARIANT_GATHER or (variant == _lib.VARIANT_AUTO and A == 1 and N >= 4096 and self.num_intervals >= 24)
@@ -305,6 +306,7 @@ class TimeSeriesEnv(BaseObject):
             self._terminated.data_ptr() if self._terminated is not None else None,
             self._ep_return.data_ptr() if self._ep_return is not None else None,
             self._ep_len.data_ptr() if self._ep_len is not None else None,
+            self._sched.data_ptr() if table is not None else None,
         )
         self._pp, self._ps, self._pst = C.byref(self._params), C.byref(self._cseries), C.byref(self._cstate)
         if self.random_reset == "last" and base + N == total:
@@ -558,7 +560,7 @@ class TimeSeriesEnv(BaseObject):
 
     def kernel_name(self) -> str:
         """Which kernel step() launches for this env's shape (diagnostics)."""
-        return self._L.fe_step_kernel_name(self._pp, self._ps).decode()
+        return self._L.fe_step_kernel_name(self._pp, self._ps, self._pst).decode()
 
     def stats(self) -> Dict[str, torch.Tensor]:
         """Device-side episode statistics accumulated since the last clear (track_stats=True)."""

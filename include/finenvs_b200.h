@@ -47,7 +47,7 @@ extern "C" {
 #define FE_VARIANT_PIPE 4   /* persistent warp-specialised pipeline (bookkeeper / mover warps, multi-stage rings) */
 #define FE_VARIANT_SPLIT 6  /* two launches: thread-per-env bookkeeping, then warp-per-env streaming with fully coalesced stores */
 #define FE_VARIANT_GATHER 8 /* persistent pipeline whose windows arrive by TMA gather4 from the observation-layout table
-                               (FeSeries.obs_table, fe_obs_table_build) and leave by bulk stores */
+                               (FeSeries.obs_table, fe_obs_table_build; needs FeState.sched) and leave by bulk stores */
 /* (5 and 7 were the round-1 "scatter" and "rows" experiments; both measured slower everywhere and were removed) */
 
 typedef struct FeParams {
@@ -93,6 +93,9 @@ typedef struct FeState {
     uint8_t *terminated; /* (N,)   evaluate only :272 (may be NULL otherwise) */
     float *ep_return;    /* (N,)   evaluate: :275; training: running episode return when stats != NULL */
     int32_t *ep_len;     /* (N,)   running episode length when stats != NULL (may be NULL) */
+    unsigned int *sched; /* optional (NULL: none) 2 zero-initialised words of scratch owned by this env: the gather variant's
+                            tile counter (its blocks claim tiles; the last block out rewinds it).  Launches that share it must
+                            not run concurrently — an env's steps never do. */
 } FeState;
 
 /* Device-side episode statistics, accumulated with one atomic per thread block (extension; the
@@ -117,9 +120,9 @@ int fe_tile_envs(int32_t window, int32_t out_f64, int32_t device);
  * 0 if the window does not fit (the tile / direct variants are used instead). */
 int fe_pipe_envs(int32_t window, int32_t out_f64, int32_t stream_flavour);
 
-/* Name of the kernel fe_step / fe_observe will launch for these parameters and this series (s may be NULL: as if
- * obs_table were NULL).  Diagnostics, bench.py. */
-const char *fe_step_kernel_name(const FeParams *p, const FeSeries *s);
+/* Name of the kernel fe_step / fe_observe will launch for these parameters, this series and this state (s / st may be
+ * NULL: as if obs_table / sched were NULL).  Diagnostics, bench.py. */
+const char *fe_step_kernel_name(const FeParams *p, const FeSeries *s, const FeState *st);
 
 /* Observation-layout table of the gather variant (replaces the (N,L,4) gather + cat of get_log_return_observations /
  * reset, :423-445, on the read side): the (T,4) log-returns as 5-value rows [lr0..lr3, hole for the position feature],

@@ -40,7 +40,7 @@ def test_struct_layouts_match_the_header(built):
     # sizes implied by the header's field lists (LP64): a silent mismatch would corrupt every call
     assert ctypes.sizeof(built.FeParams) == 4 * 8 + 4 * 4 + 4 * 8 + 8 + 6 * 4
     assert ctypes.sizeof(built.FeSeries) == 5 * 8
-    assert ctypes.sizeof(built.FeState) == 9 * 8
+    assert ctypes.sizeof(built.FeState) == 10 * 8
     assert built.STATS_BYTES == 6 * 8
 
 
@@ -109,8 +109,9 @@ def test_kernel_choice_policy(built):
 
     def name(N=1 << 20, W=60, A=1, rows=258048, f64=0, variant=built.VARIANT_AUTO, table=False):
         p = built.FeParams(N, 0, N, rows, W, 1024, A, 5, 10000.0, 0.01, 1.5, 0.25, 1, built.RESET_ALL, 1, 0, f64, variant, 0)
-        s = built.FeSeries(16, 16, 16, 16, 4096 if table else None)    # only obs_table == NULL matters to the policy
-        return L.fe_step_kernel_name(ctypes.byref(p), ctypes.byref(s)).decode()
+        s = built.FeSeries(16, 16, 16, 16, 4096 if table else None)    # only obs_table / sched == NULL matter to the policy
+        st = built.FeState(16, 16, 16, 16, 16, 16, None, None, None, 4096 if table else None)
+        return L.fe_step_kernel_name(ctypes.byref(p), ctypes.byref(s), ctypes.byref(st)).decode()
 
     assert name(table=True) == "fe_gather_kernel<float>"                      # BASELINE config 2 with the staged obs table
     assert name() == "fe_pipe_kernel<float,cached>"                           # ... without it: the round-1 kernel
