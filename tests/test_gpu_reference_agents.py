@@ -47,19 +47,18 @@ def test_reference_ppo_lstm_agent_trains_on_the_dropin(reference_tree):
                          write_to_csv=False)
     states = env.reset()
     assert states.shape == (num_envs, 4, 5)
-    trained, last_samples, seen = 0, None, []
+    trained, last_samples = 0, None
     for it in range(150):                                             # :22-30, two train() calls at 64 steps per batch
         (actions, log_probs, values) = agent.step(states)
+        held = states.clone()
         (next_states, rewards, dones, _) = env.step(actions)
-        assert next_states.data_ptr() not in seen                     # fresh tensor: the reference Buffer keeps them all
-        seen.append(next_states.data_ptr())
-        agent.store(states, actions, rewards, dones, log_probs, values)
+        assert torch.equal(states, held)                              # step() returns a fresh tensor: the observation in hand
+        agent.store(states, actions, rewards, dones, log_probs, values)   # (and those the reference Buffer cat'ed) stay intact
         states = next_states
         if agent.get_buffer_size() >= batch_size:
             before = [p.detach().clone() for p in agent.actor.parameters()]
             last_samples = agent.train(states)
             trained += 1
-            seen.clear()
             assert any(not torch.equal(a, b) for a, b in zip(before, agent.actor.parameters())), "train() changed nothing"
             assert agent.get_buffer_size() == 0
     assert trained == 2
