@@ -603,7 +603,7 @@ fe_pipe_kernel(const FeParams p, const FeSeries s, const FeState st, const Const
                 fence_proxy_async_smem();
                 named_bar_sync(1, kMovers); // out tile complete, descriptor consumed
                 if (mtid == 0) {
-                    bulk_store(dst, smem_u32(out_tile), (uint32_t)out_bytes);
+                    bulk_store_hint(dst, smem_u32(out_tile), (uint32_t)out_bytes, l2_policy_evict_first());
                     bulk_commit();
                 }
             } else { // ragged last tile
@@ -654,7 +654,7 @@ fe_pipe_kernel(const FeParams p, const FeSeries s, const FeState st, const Const
 //                               and issues the gather of unit i + S into it.
 // ------------------------------------------------------------------------------------------
 #ifndef FE_GATHER_BOOK
-#define FE_GATHER_BOOK 8
+#define FE_GATHER_BOOK 6 /* measured c2: 6 -> 0.2525 ms, 8 -> 0.2655 ms (profiles/r02_gather_README.txt) */
 #endif
 #ifndef FE_GATHER_MOVE
 #define FE_GATHER_MOVE 12
@@ -694,10 +694,12 @@ template <typename OutT> __host__ __device__ inline size_t gather_smem_bytes(int
     return kGaBarBytes + gather_desc_bytes<OutT>() + (size_t)kGaMove * S * ga_slot_pitch(W, sizeof(OutT) == 8);
 }
 
-__device__ __forceinline__ void tma_gather4(uint32_t dst_smem, const CUtensorMap *map, int r0, int r1, int r2, int r3, uint32_t bar) {
+__device__ __forceinline__ void tma_gather4(uint32_t dst_smem, const CUtensorMap *map, int r0, int r1, int r2, int r3, uint32_t bar,
+                                            uint64_t policy) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
-        ::"r"(dst_smem), "l"(map), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar)
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%2, %3, %4, %5, %6}], [%7], %8;"
+        ::"r"(dst_smem), "l"(map), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar), "l"(policy)
         : "memory");
 }
 
@@ -831,6 +833,7 @@ fe_gather_kernel(const __grid_constant__ CUtensorMap tmap, const FeParams p, con
 #pragma unroll
         for (int kk = 0; kk < kRounds; ++kk) round_mask |= (uint32_t)(lane + 32 * kk < W) << kk;
         const uint32_t env_stride = (uint32_t)W * 5; // values per env
+        const uint64_t keep = l2_policy_evict_last(), stream_out = l2_policy_evict_first();
         // unit i of this mover = group (m + i * kGaMove) % 8 of the block's sequence slot (m + i * kGaMove) / 8
         static_assert((kGaQ & (kGaQ - 1)) == 0, "kGaQ must be a power of two");
         int iss_u = m, iss_si = 0; // lane 0: next unit to issue (unit number within the block, slot)
@@ -849,7 +852,8 @@ fe_gather_kernel(const __grid_constant__ CUtensorMap tmap, const FeParams p, con
 #endif
             {
                 mbar_arrive_expect_tx(slot_full(m, iss_si), unit_b);
-                tma_gather4(smem_u32(slots + (size_t)iss_si * pitch), &tmap, rows4.x, rows4.y, rows4.z, rows4.w, slot_full(m, iss_si));
+                tma_gather4(smem_u32(slots + (size_t)iss_si * pitch), &tmap, rows4.x, rows4.y, rows4.z, rows4.w, slot_full(m, iss_si),
+                            keep);
             }
 #ifdef FE_GATHER_NOLOAD
             mbar_arrive(slot_full(m, iss_si));
@@ -907,7 +911,7 @@ fe_gather_kernel(const __grid_constant__ CUtensorMap tmap, const FeParams p, con
                 if (nv > 0)
 #endif
                 {
-                    bulk_store(obs + (size_t)env0 * W * 5, smem_u32(slot), (uint32_t)nv * row_b);
+                    bulk_store_hint(obs + (size_t)env0 * W * 5, smem_u32(slot), (uint32_t)nv * row_b, stream_out);
                     bulk_commit();
                 }
                 mbar_arrive(desc_free(q)); // this unit's descriptor entries are consumed
@@ -1441,7 +1445,7 @@ fe_portfolio_stream_kernel(const FeParams p, const FeSeries s, OutT *__restrict_
             fence_proxy_async_smem();
             __syncthreads(); // out tile complete, in tile fully consumed
             if (tid == 0) {
-                bulk_store(d, smem_u32(out_tile), (uint32_t)((size_t)n * 5 * sizeof(OutT)));
+                bulk_store_hint(d, smem_u32(out_tile), (uint32_t)((size_t)n * 5 * sizeof(OutT)), l2_policy_evict_first());
                 bulk_commit();
                 if (c + 2 < nchunks) load_chunk(c + 2);
             }
