@@ -15,9 +15,10 @@ at the mercy of a clock ramp.
 
 value    = device-resident throughput through TimeSeriesEnv.step_into (caller-owned outputs, actions in HBM).
 public_step = the same loop through the drop-in call TimeSeriesEnv.step(actions) (allocates obs/rewards/dones).
-e2e      = the same metric through the host-buffer C-ABI call fe_step_host (TimeSeriesEnv.step_host): per step
-           4N bytes of actions pinned-host -> HBM and 8N bytes (rewards f32 + dones i32) HBM -> pinned host; the
-           observation stays in HBM for the policy.
+e2e      = the same metric through the host-buffer C-ABI call fe_step_host_packed (TimeSeriesEnv.step_host(packed_dones=True)):
+           per step 4N bytes of actions pinned-host -> HBM and 4N (rewards f32) + N/8 (dones, 1 bit per env) bytes HBM ->
+           pinned host; the observation stays in HBM for the policy.  e2e.int32_dones = the same through fe_step_host
+           (dones as int32: 8N bytes back).
 roofline = bytes that must cross DRAM per launch / average launch duration, against MEASURED_PEAKS.json hbm_gbs:
            the algorithmic bytes (2264 B per env-step at A=1, W=60, f32 obs) MINUS the window reads when
            the log-return table is L2-resident (c2, c3: those reads never reach DRAM, so counting them gave a
@@ -494,14 +495,25 @@ def measure_workload(torch, par, loader, timer, workload, N, W, rank, world, loc
         check = [0.0]
 
         def host_step(i):
-            _, r_h, d_h, _ = env.step_host(ring_host[i % 4])
+            _, r_h, d_h, _ = env.step_host(ring_host[i % 4], packed_dones=True)
             check[0] += float(r_h[0]) + int(d_h[0])   # the host reads the step's result
 
         e2e = summarize(timer.blocks(host_step, steps, warmup, nblocks, wall=True), steps, total)
-        h2d, d2h = env.host_bytes_per_step()
+        h2d, d2h = env.host_bytes_per_step(packed_dones=True)
         out["e2e"] = {"value": e2e["value"], "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                       "ms_per_step": e2e["ms_per_step"], "timing": e2e["timing"],
-                      "api": "TimeSeriesEnv.step_host -> fe_step_host (pinned host buffers)"}
+                      "api": "TimeSeriesEnv.step_host(packed_dones=True) -> fe_step_host_packed (pinned host buffers; rewards f32, "
+                             "dones 1 bit per env)"}
+        launches += launches_per_step * steps * nblocks   # the persistent kernels pack the dones themselves
+
+        def host_step_i32(i):
+            _, r_h, d_h, _ = env.step_host(ring_host[i % 4])
+            check[0] += float(r_h[0]) + int(d_h[0])
+
+        e2e32 = summarize(timer.blocks(host_step_i32, steps, warmup, nblocks, wall=True), steps, total)
+        h2d32, d2h32 = env.host_bytes_per_step()
+        out["e2e"]["int32_dones"] = {"value": e2e32["value"], "ms_per_step": e2e32["ms_per_step"], "h2d_bytes_per_step": h2d32,
+                                     "d2h_bytes_per_step": d2h32, "api": "TimeSeriesEnv.step_host -> fe_step_host"}
         launches += launches_per_step * steps * nblocks
     out["gpu_launches"] = launches
     out["meta"] = meta

@@ -56,6 +56,7 @@ struct Consts {
     // optional second destination of rewards / dones (fe_step_host's zero-copy mode: mapped pinned host memory)
     void *rewards_mirror;
     int32_t *dones_mirror;
+    uint32_t *dones_bits_mirror; // fe_step_host_packed: 1 bit per env, written per 32-env tile by the persistent kernels
 };
 
 Consts make_consts(const FeParams &p) {
@@ -71,6 +72,7 @@ Consts make_consts(const FeParams &p) {
     k.SB = p.starting_balance;
     k.rewards_mirror = nullptr;
     k.dones_mirror = nullptr;
+    k.dones_bits_mirror = nullptr;
     return k;
 }
 
@@ -515,6 +517,10 @@ fe_pipe_kernel(const FeParams p, const FeSeries s, const FeState st, const Const
                 d_row0[q * TE + lane] = r.row0;
                 reinterpret_cast<OutT *>(d_pf + q * TE)[lane] = (OutT)r.posfeat;
             }
+            if (!kObserve && k.dones_bits_mirror) { // only set when TE == 32: the tile is one word of the bit-packed dones
+                const unsigned word = __ballot_sync(0xFFFFFFFFu, active && r.done);
+                if (lane == 0) k.dones_bits_mirror[env0 >> 5] = word;
+            }
             if (!kObserve) accumulate_stats(stats, r, active);
             __syncwarp();
             if (lane == 0) mbar_arrive(desc_full(q)); // release: descriptor visible to the movers
@@ -806,6 +812,10 @@ fe_gather_kernel(const __grid_constant__ CUtensorMap tmap, const FeParams p, con
             d_row[q * 32 + lane] = (int32_t)((r.row0 & ((1 << shift) - 1)) * rows_per_phase + (r.row0 >> shift));
             d_pf[q * 32 + lane] = (OutT)r.posfeat;
             if (lane == 0) d_tile[q] = t;
+            if (!kObserve && k.dones_bits_mirror) { // tile t = envs [32t, 32t + 32) = word t of the bit-packed dones
+                const unsigned word = __ballot_sync(0xFFFFFFFFu, active && r.done);
+                if (lane == 0) k.dones_bits_mirror[t] = word;
+            }
             if (!kObserve) accumulate_stats(stats, r, active);
             __syncwarp();
             if (lane == 0) mbar_arrive(desc_full(q)); // release: descriptor visible to the movers
@@ -1710,7 +1720,8 @@ int gather_tensor_map(const void *table, int64_t total_rows, int inner_bytes, in
 template <typename OutT, bool kObserve>
 int launch(const FeParams &p, const FeSeries &s, const FeState &st, const float *actions, void *obs, void *rewards,
            int32_t *dones, FeStats *stats, uint64_t step, cudaStream_t stream, const uint64_t *step_dev = nullptr,
-           void *rewards_mirror = nullptr, int32_t *dones_mirror = nullptr) {
+           void *rewards_mirror = nullptr, int32_t *dones_mirror = nullptr, uint32_t *dones_bits_mirror = nullptr,
+           bool *packed_inline = nullptr) {
     Consts k = make_consts(p);
     k.rewards_mirror = rewards_mirror;
     k.dones_mirror = dones_mirror;
@@ -1718,6 +1729,11 @@ int launch(const FeParams &p, const FeSeries &s, const FeState &st, const float 
     int rc = device_sm_count(p.device, &sms);
     if (rc) return rc;
     const StepChoice c = choose_kernel(p, s.obs_table && st.sched, sizeof(OutT) == 8, sms);
+    // the persistent kernels with 32-env tiles pack the dones themselves (one ballot per tile); otherwise the caller runs
+    // fe_pack_dones_kernel after the step
+    const bool inline_pack = dones_bits_mirror && (c.kern == K_GATHER || (c.kern == K_PIPE && c.te == 32));
+    if (inline_pack) k.dones_bits_mirror = dones_bits_mirror;
+    if (packed_inline) *packed_inline = inline_pack;
     switch (c.kern) {
     case K_ERR_SMEM: return FE_ESMEM;
     case K_ERR_TABLE: return FE_EINVAL;
@@ -2072,12 +2088,14 @@ static int step_host_impl(const FeParams *p, const FeSeries *s, const FeState *s
         if (ok && kk != K_TILE && kk != K_DIRECT) {
             const float *a = (const float *)aa.devicePointer;
             int32_t *dmirror = dones_host ? (int32_t *)ad.devicePointer : nullptr;
+            uint32_t *bmirror = dones_bits_host ? (uint32_t *)ad.devicePointer : nullptr;
+            bool packed_inline = false;
             rc = p->out_f64 ? launch<double, false>(*p, *s, *st, a, obs_dev, rewards_dev, dones_dev, stats_dev, step_counter, q,
-                                                    nullptr, ar.devicePointer, dmirror)
+                                                    nullptr, ar.devicePointer, dmirror, bmirror, &packed_inline)
                             : launch<float, false>(*p, *s, *st, a, obs_dev, rewards_dev, dones_dev, stats_dev, step_counter, q,
-                                                   nullptr, ar.devicePointer, dmirror);
+                                                   nullptr, ar.devicePointer, dmirror, bmirror, &packed_inline);
             if (rc) return rc;
-            if (dones_bits_host) {
+            if (dones_bits_host && !packed_inline) {
                 fe_pack_dones_kernel<<<(unsigned)((n + 255) / 256), 256, 0, q>>>(dones_dev, n, (uint32_t *)ad.devicePointer);
                 if ((rc = (int)cudaGetLastError())) return rc;
             }

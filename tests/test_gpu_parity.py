@@ -548,14 +548,16 @@ def test_pipe_variant_vs_oracle(W, N, dtype, variant):
     assert n_done > 0 and int(env.stats()["n_done"].item()) == n_done
 
 
-@pytest.mark.parametrize("N,A,dtype", [(70001, 1, torch.float32), (40000, 1, torch.float64), (9000, 1, torch.float32),
-                                       (33000, 3, torch.float32), (19007, 1, torch.float32)])
-def test_step_host_pipeline_equals_device_step(N, A, dtype):
+@pytest.mark.parametrize("N,A,dtype,W", [(70001, 1, torch.float32, 12), (40000, 1, torch.float64, 12), (9000, 1, torch.float32, 12),
+                                         (33000, 3, torch.float32, 12), (19007, 1, torch.float32, 12),
+                                         (40003, 1, torch.float32, 24),     # gather kernel: dones packed by the bookkeepers
+                                         (40003, 1, torch.float32, 26),     # pipe kernel, 32-env tiles: same
+                                         (30011, 1, torch.float64, 130)])   # pipe kernel, 4-env tiles: separate pack kernel
+def test_step_host_pipeline_equals_device_step(N, A, dtype, W):
     """fe_step_host cuts the envs into chunks on side streams (upload / kernel / download overlapped): same
     results as the one-launch device-resident step, for ragged chunk counts, both dtypes, A > 1, with statistics."""
     from finenvs_b200.data import loader
 
-    W = 12
     if A == 1:
         prices, seg_start, seg_len = _c1_series(W, days=50, bars=30, sigma=0.04, seed=N)
     else:
