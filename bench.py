@@ -144,7 +144,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.01)   # NVML queries take driver locks: poll gently, the timed legs last seconds in total
 
     def __enter__(self):
         if self._nv is not None:

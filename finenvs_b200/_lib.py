@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("FINENVS_B200_LIB") or os.path.join(_HERE, "libfinenvs
 
 RESET_KEEP, RESET_LAST, RESET_ALL = 0, 1, 2
 VARIANT_AUTO, VARIANT_TILE, VARIANT_DIRECT, VARIANT_PORTFOLIO, VARIANT_PIPE, VARIANT_SPLIT, VARIANT_GATHER = 0, 1, 2, 3, 4, 6, 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class FeParams(C.Structure):

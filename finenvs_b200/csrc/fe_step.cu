@@ -56,7 +56,14 @@ struct Consts {
     // optional second destination of rewards / dones (fe_step_host's zero-copy mode: mapped pinned host memory)
     void *rewards_mirror;
     int32_t *dones_mirror;
-    uint32_t *dones_bits_mirror; // fe_step_host_packed: 1 bit per env, written per 32-env tile by the persistent kernels
+    // fe_step_host_packed: 1 bit per env, one word per 32-env tile, written by the persistent kernels' bookkeepers.
+    // dones_bits_out is where they write it.  Writing the words straight to mapped host memory means 32 Ki separate 4-byte
+    // PCIe writes per 1 Mi-env step (partial cache lines for the host: measured 0.32 ms per step against 0.27 ms with int32
+    // dones), so the words go to a staging buffer in HBM and leave in 128-byte lines: the gather kernel's
+    // blocks copy the staging buffer to dones_bits_host (dones_bits_host != nullptr) once all bookkeeping is done, the
+    // other kernels are followed by fe_flush_bits_kernel.
+    uint32_t *dones_bits_out;
+    uint32_t *dones_bits_host;
 };
 
 Consts make_consts(const FeParams &p) {
@@ -72,7 +79,8 @@ Consts make_consts(const FeParams &p) {
     k.SB = p.starting_balance;
     k.rewards_mirror = nullptr;
     k.dones_mirror = nullptr;
-    k.dones_bits_mirror = nullptr;
+    k.dones_bits_out = nullptr;
+    k.dones_bits_host = nullptr;
     return k;
 }
 
@@ -517,9 +525,9 @@ fe_pipe_kernel(const FeParams p, const FeSeries s, const FeState st, const Const
                 d_row0[q * TE + lane] = r.row0;
                 reinterpret_cast<OutT *>(d_pf + q * TE)[lane] = (OutT)r.posfeat;
             }
-            if (!kObserve && k.dones_bits_mirror) { // only set when TE == 32: the tile is one word of the bit-packed dones
+            if (!kObserve && k.dones_bits_out) { // only set when TE == 32: the tile is one word of the bit-packed dones
                 const unsigned word = __ballot_sync(0xFFFFFFFFu, active && r.done);
-                if (lane == 0) k.dones_bits_mirror[env0 >> 5] = word;
+                if (lane == 0) k.dones_bits_out[env0 >> 5] = word;
             }
             if (!kObserve) accumulate_stats(stats, r, active);
             __syncwarp();
@@ -778,8 +786,15 @@ fe_gather_kernel(const __grid_constant__ CUtensorMap tmap, const FeParams p, con
         long long acc[16] = {0};
         int ntl = 0;
 #endif
-        for (;;) {
-            int n = 0, t = 0; // sequence slot of this block, tile of the grid (>= ntiles_all: none left)
+        // With the actions in mapped host memory (fe_step_host: k.rewards_mirror is set) the action load is a PCIe read of
+        // ~2 us.  There a claim is taken one tile AHEAD of the tile being computed and the first-hop loads of the claimed
+        // tile (action and per-env state) are issued at once, in flight while the current tile is computed, so that the
+        // read no longer sits in every tile's dependency chain (measured c2, 1 Mi envs, zero-copy: kernel 0.253 -> 0.2305 ms,
+        // the device-resident time; profiles/r02_e2e_probe_ahead.txt).  Device-resident launches claim tile by tile: holding
+        // a second claim cost them 0.5 % (tail balance).
+        const bool ahead = !kObserve && k.rewards_mirror != nullptr;
+        auto take_claim = [&](int &n, int &t) { // sequence slot of this block, tile of the grid (>= ntiles_all: none left)
+            n = 0; t = 0;
             if (lane == 0) {
                 while (atomicCAS(&claim[0], 0u, 1u) != 0u) {}
                 n = (int)claim[1];
@@ -790,7 +805,23 @@ fe_gather_kernel(const __grid_constant__ CUtensorMap tmap, const FeParams p, con
             }
             n = __shfl_sync(0xFFFFFFFFu, n, 0);
             t = __shfl_sync(0xFFFFFFFFu, t, 0);
+        };
+        auto first_hop = [&](int t, EnvLoads &ld) {
+            const int64_t i = (int64_t)t * 32 + lane;
+            if (!kObserve && t < ntiles_all && i < p.num_envs) ld = env_load_state(st, actions, i);
+        };
+        int n, t, n_next = 0, t_next = 0;
+        EnvLoads ld, ld_next;
+        ld.seg = 0; ld.ptr = 0; ld.cash = 0.0f; ld.lng = 0.0f; ld.sht = 0.0f; ld.act = 0.0f; ld.margin = 0.0;
+        ld_next = ld;
+        take_claim(n, t);
+        first_hop(t, ld);
+        for (;;) {
             const int q = n & (kGaQ - 1);
+            if (ahead && t < ntiles_all) { // the next claim and its loads, before this tile's wait and arithmetic
+                take_claim(n_next, t_next);
+                first_hop(t_next, ld_next);
+            }
             GA_CLK(c0);
             if (lane == 0) mbar_wait(desc_free(q), ((n / kGaQ) & 1) ^ 1); // first lap passes immediately
             __syncwarp();
@@ -806,15 +837,15 @@ fe_gather_kernel(const __grid_constant__ CUtensorMap tmap, const FeParams p, con
             r.done = 0; r.newly_terminated = 0; r.fin_return = 0.0; r.fin_len = 0; r.row0 = 0; r.posfeat = 0.0;
             if (active) {
                 if (kObserve) r = env_observe(p, s, st, k, i);
-                else r = env_step<OutT>(p, s, st, k, i, actions, rewards, dones, stats != nullptr, step);
+                else r = env_compute<OutT>(p, s, st, k, i, ld, env_load_bar(p, s, ld), rewards, dones, stats != nullptr, step);
             }
             // window starting at series row row0 = copy (row0 mod P), tensor row (row0 div P) of that copy
             d_row[q * 32 + lane] = (int32_t)((r.row0 & ((1 << shift) - 1)) * rows_per_phase + (r.row0 >> shift));
             d_pf[q * 32 + lane] = (OutT)r.posfeat;
             if (lane == 0) d_tile[q] = t;
-            if (!kObserve && k.dones_bits_mirror) { // tile t = envs [32t, 32t + 32) = word t of the bit-packed dones
+            if (!kObserve && k.dones_bits_out) { // tile t = envs [32t, 32t + 32) = word t of the bit-packed dones
                 const unsigned word = __ballot_sync(0xFFFFFFFFu, active && r.done);
-                if (lane == 0) k.dones_bits_mirror[t] = word;
+                if (lane == 0) k.dones_bits_out[t] = word;
             }
             if (!kObserve) accumulate_stats(stats, r, active);
             __syncwarp();
@@ -824,6 +855,37 @@ fe_gather_kernel(const __grid_constant__ CUtensorMap tmap, const FeParams p, con
 #ifdef FE_GATHER_CLOCKS
             ++ntl;
 #endif
+            if (ahead) { n = n_next; t = t_next; ld = ld_next; }
+            else { take_claim(n, t); first_hop(t, ld); }
+        }
+        // Bit-packed dones (fe_step_host_packed): the words sit in the staging buffer; once EVERY bookkeeper warp of the grid
+        // has finished (counter sched[2]; the grid is persistent, one block per SM, so waiting on it cannot deadlock) each
+        // block sends its 1 / gridDim.x share to the host as full 128-byte lines — the movers are still draining their
+        // last units meanwhile.  (One block sending all 128 KB took 8 us of tail: a single SM's stores to system memory.)
+        if (!kObserve && k.dones_bits_host) {
+            if (lane == 0) {
+                __threadfence();
+                atomicAdd(&sched[2], 1u);
+            }
+            if (warp == 0) {
+                if (lane == 0) {
+                    const unsigned want = gridDim.x * (unsigned)kGaBook;
+                    while (ld_acquire_gpu(&sched[2]) < want) __nanosleep(100);
+                }
+                __syncwarp();
+                const int per = (((ntiles_all + (int)gridDim.x - 1) / (int)gridDim.x) + 31) & ~31; // whole lines per block
+                const int w_begin = (int)blockIdx.x * per;
+                const int w_end = w_begin + per < ntiles_all ? w_begin + per : ntiles_all;
+                constexpr int kBatch = 8; // loads in batches ahead of the stores: one L2 round trip per batch, not per word
+                for (int w0 = w_begin + lane; w0 < w_end; w0 += kBatch * 32) {
+                    uint32_t v[kBatch];
+#pragma unroll
+                    for (int j = 0; j < kBatch; ++j) v[j] = w0 + 32 * j < w_end ? __ldcg(k.dones_bits_out + w0 + 32 * j) : 0u;
+#pragma unroll
+                    for (int j = 0; j < kBatch; ++j)
+                        if (w0 + 32 * j < w_end) k.dones_bits_host[w0 + 32 * j] = v[j];
+                }
+            }
         }
 #ifdef FE_GATHER_CLOCKS
         if (blockIdx.x == 0 && tid == 0) { fe_gather_clk[8] = acc[8]; fe_gather_clk[9] = acc[9]; fe_gather_clk[10] = ntl; }
@@ -946,13 +1008,15 @@ fe_gather_kernel(const __grid_constant__ CUtensorMap tmap, const FeParams p, con
         if (blockIdx.x == 0 && m == 0 && lane == 0) { for (int c = 0; c < 6; ++c) fe_gather_clk[c] = acc[c]; fe_gather_clk[6] = issued; fe_gather_clk[11] = acc[11]; fe_gather_clk[12] = 0; fe_gather_clk[13] = clock64() - mover_t0; }
 #endif
     }
-    // the last block out rewinds the tile counter for the next launch (every block's claims precede its arrival here)
+    // the last block out rewinds the counters for the next launch (every block's claims, and its wait on sched[2], precede
+    // its arrival here)
     __syncthreads();
     if (tid == 0) {
         __threadfence();
         if (atomicAdd(&sched[1], 1u) == gridDim.x - 1) {
             sched[0] = 0;
             sched[1] = 0;
+            sched[2] = 0;
             __threadfence();
         }
     }
@@ -1721,7 +1785,7 @@ template <typename OutT, bool kObserve>
 int launch(const FeParams &p, const FeSeries &s, const FeState &st, const float *actions, void *obs, void *rewards,
            int32_t *dones, FeStats *stats, uint64_t step, cudaStream_t stream, const uint64_t *step_dev = nullptr,
            void *rewards_mirror = nullptr, int32_t *dones_mirror = nullptr, uint32_t *dones_bits_mirror = nullptr,
-           bool *packed_inline = nullptr) {
+           uint32_t *dones_bits_stage = nullptr, int *packed_inline = nullptr) {
     Consts k = make_consts(p);
     k.rewards_mirror = rewards_mirror;
     k.dones_mirror = dones_mirror;
@@ -1731,9 +1795,14 @@ int launch(const FeParams &p, const FeSeries &s, const FeState &st, const float 
     const StepChoice c = choose_kernel(p, s.obs_table && st.sched, sizeof(OutT) == 8, sms);
     // the persistent kernels with 32-env tiles pack the dones themselves (one ballot per tile); otherwise the caller runs
     // fe_pack_dones_kernel after the step
-    const bool inline_pack = dones_bits_mirror && (c.kern == K_GATHER || (c.kern == K_PIPE && c.te == 32));
-    if (inline_pack) k.dones_bits_mirror = dones_bits_mirror;
-    if (packed_inline) *packed_inline = inline_pack;
+    const bool inline_pack = dones_bits_mirror && dones_bits_stage && (c.kern == K_GATHER || (c.kern == K_PIPE && c.te == 32));
+    const int pack_mode = env_override("FE_PACK_MODE"); // sweeps: 1 = words straight to the host, 2 = flush by a second kernel
+    if (inline_pack) {
+        k.dones_bits_out = pack_mode == 1 ? dones_bits_mirror : dones_bits_stage;
+        if (c.kern == K_GATHER && pack_mode == 0) k.dones_bits_host = dones_bits_mirror; // sent by the kernel itself
+    }
+    // 0: the caller packs dones_dev after the step; 1: packed and already sent to the host; 2: packed into the staging buffer
+    if (packed_inline) *packed_inline = !inline_pack ? 0 : (pack_mode == 1 || (c.kern == K_GATHER && pack_mode == 0)) ? 1 : 2;
     switch (c.kern) {
     case K_ERR_SMEM: return FE_ESMEM;
     case K_ERR_TABLE: return FE_EINVAL;
@@ -1852,6 +1921,12 @@ __global__ void __launch_bounds__(256) fe_pack_dones_kernel(const int32_t *__res
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned word = __ballot_sync(0xFFFFFFFFu, i < n && dones[i] != 0);
     if ((threadIdx.x & 31) == 0 && i < n) bits[i >> 5] = word;
+}
+
+// staging buffer (HBM) -> mapped host memory: consecutive threads, consecutive words, so the bits cross PCIe in full lines
+__global__ void __launch_bounds__(256) fe_flush_bits_kernel(const uint32_t *__restrict__ stage, const int64_t nwords, uint32_t *__restrict__ host) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < nwords) host[w] = stage[w];
 }
 
 } // namespace
@@ -2089,14 +2164,19 @@ static int step_host_impl(const FeParams *p, const FeSeries *s, const FeState *s
             const float *a = (const float *)aa.devicePointer;
             int32_t *dmirror = dones_host ? (int32_t *)ad.devicePointer : nullptr;
             uint32_t *bmirror = dones_bits_host ? (uint32_t *)ad.devicePointer : nullptr;
-            bool packed_inline = false;
+            // the actions are read from the host: actions_dev (>= 4 bytes per env) is free to stage the packed bits
+            uint32_t *stage = reinterpret_cast<uint32_t *>(actions_dev);
+            int packed_inline = 0;
             rc = p->out_f64 ? launch<double, false>(*p, *s, *st, a, obs_dev, rewards_dev, dones_dev, stats_dev, step_counter, q,
-                                                    nullptr, ar.devicePointer, dmirror, bmirror, &packed_inline)
+                                                    nullptr, ar.devicePointer, dmirror, bmirror, stage, &packed_inline)
                             : launch<float, false>(*p, *s, *st, a, obs_dev, rewards_dev, dones_dev, stats_dev, step_counter, q,
-                                                   nullptr, ar.devicePointer, dmirror, bmirror, &packed_inline);
+                                                   nullptr, ar.devicePointer, dmirror, bmirror, stage, &packed_inline);
             if (rc) return rc;
-            if (dones_bits_host && !packed_inline) {
-                fe_pack_dones_kernel<<<(unsigned)((n + 255) / 256), 256, 0, q>>>(dones_dev, n, (uint32_t *)ad.devicePointer);
+            if (dones_bits_host && packed_inline != 1) {
+                const int64_t nwords = (n + 31) / 32;
+                if (packed_inline == 0)
+                    fe_pack_dones_kernel<<<(unsigned)((n + 255) / 256), 256, 0, q>>>(dones_dev, n, stage);
+                fe_flush_bits_kernel<<<(unsigned)((nwords + 255) / 256), 256, 0, q>>>(stage, nwords, (uint32_t *)ad.devicePointer);
                 if ((rc = (int)cudaGetLastError())) return rc;
             }
             return (int)cudaStreamSynchronize(q);

@@ -284,6 +284,7 @@ class TimeSeriesEnv(BaseObject):
         self._ep_return = torch.zeros(N, dtype=torch.float32, device=dev) if need_ep else None
         self._ep_len = torch.zeros(N, dtype=torch.int32, device=dev) if self.track_stats else None
         self._stats = torch.zeros(_lib.STATS_BYTES // 8, dtype=torch.int64, device=dev) if need_ep else None
+        self._stats_ptr = self._stats.data_ptr() if self._stats is not None else None   # never reallocated (zeroed in place)
         self.step_count = 0
         self._epoch = 0   # bumped by everything that changes the state other than a step (reset_all, snapshots)
         self._params = _lib.FeParams(
@@ -293,7 +294,7 @@ class TimeSeriesEnv(BaseObject):
             int(self.random_offset), int(self.evaluate), int(self.obs_dtype == torch.float64), variant,
             dev.index if dev.index is not None else torch.cuda.current_device(),
         )
-        self._sched = torch.zeros(2, dtype=torch.int32, device=dev)   # gather kernel: tile counter (FeState.sched)
+        self._sched = torch.zeros(4, dtype=torch.int32, device=dev)   # gather kernel: tile / arrival counters (FeState.sched)
         s = self.series
         # the observation-layout table is only built for envs that can use it (large populations or variant="gather")
         want_table = variant == _lib.VARIANT_GATHER or (variant == _lib.VARIANT_AUTO and A == 1 and N >= 4096 and self.num_intervals >= 24)
@@ -460,15 +461,16 @@ class TimeSeriesEnv(BaseObject):
                 torch.empty(self.num_envs, dtype=torch.int32).pin_memory(),
                 torch.zeros(4 * ((self.num_envs + 31) // 32), dtype=torch.uint8).pin_memory(),
             )
-        a_dev, r_dev, d_dev, rewards, dones, done_bits = self._host_bufs
+            self._host_ptrs = tuple(t.data_ptr() for t in self._host_bufs)   # the buffers live as long as the env
+        _, _, _, rewards, dones, done_bits = self._host_bufs
+        p_a, p_r, p_d, p_rh, p_dh, p_bh = self._host_ptrs
         obs = self._new_obs()
         self.step_count += 1
         fn = self._L.fe_step_host_packed if packed_dones else self._L.fe_step_host
         out_dones = done_bits if packed_dones else dones
         _lib.check(
-            fn(self._pp, self._ps, self._pst, actions_host.data_ptr(), a_dev.data_ptr(), obs.data_ptr(),
-               r_dev.data_ptr(), d_dev.data_ptr(), rewards.data_ptr(), out_dones.data_ptr(),
-               self._stats.data_ptr() if self._stats is not None else None, self.step_count, self._stream()),
+            fn(self._pp, self._ps, self._pst, actions_host.data_ptr(), p_a, obs.data_ptr(), p_r, p_d, p_rh,
+               p_bh if packed_dones else p_dh, self._stats_ptr, self.step_count, self._stream()),
             "fe_step_host_packed" if packed_dones else "fe_step_host",
         )
         info_dict = self.record_evaluation_metrics() if self.evaluate else {}

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define FE_ABI_VERSION 2
+#define FE_ABI_VERSION 3
 
 /* argument errors */
 #define FE_EINVAL (-1)   /* null pointer / non-positive size / unsupported num_assets */
@@ -93,9 +93,9 @@ typedef struct FeState {
     uint8_t *terminated; /* (N,)   evaluate only :272 (may be NULL otherwise) */
     float *ep_return;    /* (N,)   evaluate: :275; training: running episode return when stats != NULL */
     int32_t *ep_len;     /* (N,)   running episode length when stats != NULL (may be NULL) */
-    unsigned int *sched; /* optional (NULL: none) 2 zero-initialised words of scratch owned by this env: the gather variant's
-                            tile counter (its blocks claim tiles; the last block out rewinds it).  Launches that share it must
-                            not run concurrently — an env's steps never do. */
+    unsigned int *sched; /* optional (NULL: none) 4 zero-initialised words of scratch owned by this env: the gather variant's
+                            tile counter (its blocks claim tiles), block and bookkeeper arrival counters; the last block out
+                            rewinds them.  Launches that share it must not run concurrently — an env's steps never do. */
 } FeState;
 
 /* Device-side episode statistics, accumulated with one atomic per thread block (extension; the
