@@ -25,7 +25,9 @@ roofline = DRAM bytes per launch / average launch duration (live, CUDA events), 
            (2264 B per env-step at A=1, W=60, f32 obs, MINUS the 960 B of window reads while the table is
            L2-resident: those never reach DRAM, and counting them gave round 1 a "fraction" of 1.34) and `algorithmic_*`
            (all 2264 B).
-also     = the other BASELINE workloads measured in the same process (N=1: c4 and c3; N>1: c4), same protocol.
+also     = the other BASELINE workloads measured in the same process (N=1: c4, c3 and c5; N>1: c4 and c5), same protocol;
+           c5 = the ES population rollout (policy forward + env step + return bookkeeping per step, EvoAgent.train() per
+           generation; perturbations are stored as fp16 where the reference draws f32).
 collectives (N>1) = device time of the NCCL collectives the path uses outside the step (episode statistics
            all-reduce, ES fitness all-gather, ES gradient all-reduce).
 cpu_baseline / --impl reference = the reference's OWN TimeSeriesEnv.step (unmodified, from baseline/_ref,
@@ -79,11 +81,25 @@ WORKLOAD_NAMES = {
     "c3": "30-asset portfolio-allocation env, 65536 envs, 128-step window, transaction costs, 1 B200",
     "c2": "single-asset env, 1M envs, 60-step window, fused step kernel on 1 B200 vs reference",
     "c4": "synthetic minute-bar series of 10M timesteps, 1M envs per GPU with random start offsets, env-sharded",
+    "c5": "ES population rollout (finenvs_b200.agents.ES.EvoAgent) with 512Ki envs per GPU (4M across 8), fitness over NCCL",
 }
 
 
+_SERIES_CACHE: dict = {}
+
+
 def make_series(workload: str, W: int):
-    """Synthetic GBM OHLC (SURVEY.md §8d recipe) + segment table."""
+    """Synthetic GBM OHLC (SURVEY.md §8d recipe) + segment table.  The 10 M-row c4 series (320 MB, seconds of host time)
+    is kept for the second workload that uses it (also.c5)."""
+    if (workload, W) in _SERIES_CACHE:
+        return _SERIES_CACHE[(workload, W)]
+    out = _make_series(workload, W)
+    if workload == "c4":
+        _SERIES_CACHE[(workload, W)] = out
+    return out
+
+
+def _make_series(workload: str, W: int):
     from finenvs_b200.data import loader
     from parity_utils import gbm_ohlc
 
@@ -530,6 +546,30 @@ def measure_workload(torch, par, loader, timer, workload, N, W, rank, world, loc
     return out
 
 
+def measure_es_rollout(rank: int, world: int, local_rank: int):
+    """BASELINE config 5 at this GPU count: 512 Ki envs per GPU (4 Mi on 8), each env its own ES population member, the
+    reference's ES loop (examples/isaac_gym/ES_MLP_Isaac_Gym.py:30-38) on the drop-ins: policy forward + env step + return
+    bookkeeping per step, EvoAgent.train() (fitness all-gather, gradient all-reduce over NCCL when world > 1) per
+    generation.  tools/es_rollout.py is the same loop as a script."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import es_rollout
+
+    steps, gens, n = 64, 3, 524288
+    rec = es_rollout.run(rank, world, local_rank, envs_per_gpu=n, steps=steps, generations=gens, make_series=make_series)
+    g = rec["generations"]
+    med = float(np.median([x["ms_per_step"] for x in g]))
+    return {"workload": WORKLOAD_NAMES["c5"], "envs_per_gpu": n, "total_envs": n * world, "window": rec["window"], "assets": 1,
+            "value": n * world / (med * 1e-3), "unit": UNIT, "ms_per_step": med,
+            "what_a_step_is": "policy forward (perturbed MLP per env, window read straight from the staged 10 M-row series) + env step "
+                              "+ return bookkeeping: 3 launches, no observation tensor, no host sync",
+            "train_ms_per_generation": float(np.median([x["train_ms"] for x in g])), "steps_per_generation": steps,
+            "generations": gens, "episodes_ranked_per_generation": g[-1]["episodes_ranked"],
+            "parameters_identical_on_all_ranks": all(x["parameters_identical_on_all_ranks"] for x in g),
+            "network_shape": rec["network_shape"], "perturbation_storage": rec["perturbation_storage"],
+            "fitness_gather": rec["fitness_gather"], "kernels_per_step": rec["kernels_per_step"],
+            "gpu_launches": 3 * steps * gens}
+
+
 def measure_collectives(torch, dist, par, dev, world, N):
     """Device time (CUDA events, max over ranks) of the collectives the path uses outside the step."""
     def timed(fn, reps=20):
@@ -573,6 +613,7 @@ def main():
     ap.add_argument("--ref-widened-envs", type=int, default=65536,
                     help="second size the unmodified reference is timed at (SURVEY App. C.4 widening); 0 = native N=1024 only")
     ap.add_argument("--no-also", action="store_true", help="skip the other workloads / collectives")
+    ap.add_argument("--no-c5", action="store_true", help="skip the ES population rollout (also.c5)")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to its GPU's NUMA-local CPUs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -615,6 +656,9 @@ def main():
                        "kernel": r["roofline"]["kernel"], "frac": r["roofline"]["frac"], "dram_frac": r["roofline"]["dram_frac"],
                        "algorithmic_frac": r["roofline"]["algorithmic_frac"], "roofline": r["roofline"],
                        "gpu_launches": r["gpu_launches"]}
+        if not args.no_c5:
+            also["c5"] = measure_es_rollout(rank, world, local_rank)
+        _SERIES_CACHE.clear()
         if world > 1:
             collectives = measure_collectives(torch, dist, par, dev, world, args.envs)
 

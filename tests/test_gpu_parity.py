@@ -348,17 +348,29 @@ def _check_obs_properties(env, obs, ptr_before_reset, seg_before_reset):
     n = obs.shape[0]
     o = obs.view(n, W, A, 5)
     row0 = s.seg_start[seg_before_reset.long()] + ptr_before_reset.long()
-    idx = torch.randint(0, n, (4096,), device=obs.device)
-    rows = row0[idx, None] + torch.arange(W, device=obs.device)[None, :]
-    want = s.logret.view(s.num_rows, A, 4)[rows]                     # (4096, W, A, 4)
-    assert torch.equal(o[idx][..., :4], want)
+    table = s.logret.view(s.num_rows, A, 4)
+    steps = torch.arange(W, device=obs.device)[None, :]
+    chunk = max(1, (1 << 26) // (W * A * 4))                         # EVERY env, 64 Mi values (256 MB f32) at a time
+    for lo in range(0, n, chunk):
+        rows = row0[lo:lo + chunk, None] + steps
+        assert torch.equal(o[lo:lo + chunk, ..., :4], table[rows]), f"window of an env in [{lo}, {lo + chunk})"
     assert torch.equal(o[..., 4], o[:, :1, :, 4].expand(-1, W, -1))
+
+
+def _assert_full_obs_equals_oracle(obs, o_ref):
+    """The WHOLE observation of one step, bit for bit (windows and position-feature values of every env)."""
+    got = obs.cpu().numpy().reshape(-1)
+    want = np.asarray(o_ref).reshape(-1)
+    assert got.dtype == want.dtype and got.shape == want.shape
+    assert np.array_equal(got.view(np.uint32 if got.itemsize == 4 else np.uint64), want.view(np.uint32 if want.itemsize == 4 else np.uint64))
 
 
 def test_config2_full_size_1M_envs():
     """BASELINE config 2 at full size: 1 Mi envs, W=60.  Three steps of the FULL population against the oracle
-    (state, rewards, dones exact; obs through its gather property) and a 65 536-env slice in lock-step for
-    2x252 steps (every env auto-resets at least twice)."""
+    (state, rewards, dones exact; the whole 1.26 GB observation bit for bit on the first and the last of them, every env's
+    window through the gather property on all three) and a 65 536-env slice in lock-step for 2x252 steps (every env
+    auto-resets at least twice).  The oracle is fed the log-return table the GPU staged (series.logret64): the table itself
+    is pinned to the reference by test_log_returns_kernel_vs_reference_values."""
     from oracle import oracle as orc
     from finenvs_b200.data import loader
 
@@ -375,12 +387,15 @@ def test_config2_full_size_1M_envs():
         a = torch.rand((N, 1), generator=g) * 2 - 1
         ptr0, seg0 = env._ptr.clone() + 1, env._seg.clone()
         obs, r, d, _ = env.step(a.cuda())
-        _, r_ref, d_ref, _ = ref.step(a.numpy(), want_obs=False)
+        o_ref, r_ref, d_ref, _ = ref.step(a.numpy(), want_obs=t != 1)
         assert np.array_equal(d.cpu().numpy(), d_ref) and np.array_equal(r.cpu().numpy(), r_ref)
         for key, t_gpu in (("seg", env._seg), ("ptr", env._ptr), ("cash", env._cash), ("long_sh", env._long),
                            ("short_sh", env._short), ("margin", env._margin)):
             assert np.array_equal(t_gpu.cpu().numpy(), getattr(ref, key)), key
         _check_obs_properties(env, obs, ptr0, seg0)
+        if t != 1:
+            _assert_full_obs_equals_oracle(obs, o_ref)
+        del o_ref
         assert int((env._long * env._short).abs().sum()) == 0          # never long and short at once (:311-314)
         assert bool((env._ptr + W < series.seg_len[env._seg.long()]).all())  # a bar always remains to step onto
         total_done += int(d_ref.sum())
@@ -424,11 +439,14 @@ def test_config4_minute_bars_8M_population_shard():
         a = torch.rand((n, 1), generator=g) * 2 - 1
         ptr0, seg0 = env._ptr.clone() + 1, env._seg.clone()
         obs, r, d, _ = env.step(a.cuda())
-        _, r_ref, d_ref, _ = ref.step(a.numpy(), want_obs=False)
+        o_ref, r_ref, d_ref, _ = ref.step(a.numpy(), want_obs=t == 3)
         assert np.array_equal(d.cpu().numpy(), d_ref) and np.array_equal(r.cpu().numpy(), r_ref)
         assert np.array_equal(env._seg.cpu().numpy(), ref.seg) and np.array_equal(env._ptr.cpu().numpy(), ref.ptr)
         assert np.array_equal(env._cash.cpu().numpy(), ref.cash)
         _check_obs_properties(env, obs, ptr0, seg0)
+        if t == 3:   # the whole observation of the last step (after some envs redrew segment and offset), bit for bit
+            _assert_full_obs_equals_oracle(obs, o_ref)
+        del o_ref
         assert d_ref.sum() > 0                                          # offsets spread the episode ends
 
 
@@ -477,7 +495,9 @@ def test_auto_picks_the_kernels_documented_in_design():
 
 
 def test_config3_full_size_portfolio():
-    """BASELINE config 3 at full size: 30 assets, 65 536 envs, W=128 (obs is 5 GB per step)."""
+    """BASELINE config 3 at full size: 30 assets, 65 536 envs, W=128 (obs is 5 GB per step): state, rewards, dones exact on
+    three steps, every env's windows through the gather property, and the whole observation of the third step bit for
+    bit against the multi-asset oracle (itself cross-checked by tests/test_portfolio_restatement.py)."""
     from oracle import oracle as orc
     from finenvs_b200.data import loader
 
@@ -492,13 +512,15 @@ def test_config3_full_size_portfolio():
         a = torch.rand((N, A), generator=g) * 2 - 1
         ptr0, seg0 = env._ptr.clone() + 1, env._seg.clone()
         obs, r, d, _ = env.step(a.cuda())
-        _, r_ref, d_ref, _ = ref.step(a.numpy(), want_obs=False)
+        o_ref, r_ref, d_ref, _ = ref.step(a.numpy(), want_obs=t == 2)
         assert np.array_equal(d.cpu().numpy(), d_ref) and np.array_equal(r.cpu().numpy(), r_ref)
         assert np.array_equal(env._cash.cpu().numpy(), ref.cash)
         assert np.array_equal(env._margin.cpu().numpy(), ref.margin.reshape(-1))
         assert np.array_equal(env._long.cpu().numpy(), ref.long_sh.reshape(-1))
         _check_obs_properties(env, obs, ptr0, seg0)
-        del obs
+        if t == 2:   # all 5 GB of the last step's observation, bit for bit
+            _assert_full_obs_equals_oracle(obs, o_ref)
+        del obs, o_ref
 
 
 def test_flat_obs_and_es_env_args():

@@ -36,56 +36,48 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--envs-per-gpu", type=int, default=524288)
-    ap.add_argument("--eval-envs-per-gpu", type=int, default=0)
-    ap.add_argument("--steps", type=int, default=64)
-    ap.add_argument("--generations", type=int, default=3)
-    ap.add_argument("--window", type=int, default=60)
-    ap.add_argument("--hidden", type=int, nargs="*", default=[8])
-    ap.add_argument("--workload", default="c4", choices=["c2", "c4"])
-    ap.add_argument("--mode", default="lazy", choices=["lazy", "dense"])
-    ap.add_argument("--sigma", type=float, default=0.05)
-    ap.add_argument("--lr", type=float, default=0.01)
-    args = ap.parse_args()
-
-    import bench
+def run(rank, world, local_rank, envs_per_gpu=524288, eval_envs_per_gpu=0, steps=64, generations=3, window=60, hidden=(8,),
+        workload="c4", mode="lazy", sigma=0.05, lr=0.01, make_series=None):
+    """The rollout + train loop on this rank's GPU (process group already initialised when world > 1); returns the record
+    (every rank gets the same per-generation numbers: times are the max over ranks).  bench.py calls this for its
+    `also.c5` block."""
+    if make_series is None:
+        import bench
+        make_series = bench.make_series
     from finenvs_b200 import parallel as par
     from finenvs_b200.agents.ES import EvoAgent
     from finenvs_b200.data import loader
     from finenvs_b200.environments import TimeSeriesEnv
 
-    rank, world, local_rank = par.init_distributed("nccl")
-    torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    W, n, n_eval = args.window, args.envs_per_gpu, args.eval_envs_per_gpu
+    W, n, n_eval = window, envs_per_gpu, eval_envs_per_gpu
     assert (n - n_eval) % 2 == 0, "mirrored sampling needs an even training population per GPU"
     total = n * world
     pairs = (n - n_eval) // 2
-    prices, seg_start, seg_len, _ = bench.make_series(args.workload, W)
+    prices, seg_start, seg_len, _ = make_series(workload, W)
     series = loader.stage_series(prices, seg_start, seg_len, W, str(dev), torch.float32)
+    del prices
     env = TimeSeriesEnv("es", num_intervals=W, device_id=local_rank, series=series, num_envs=n, env_id_base=rank * n,
                         total_envs=total, seed=5, random_reset="all", random_offset=True, flat_obs=True,
                         num_eval_envs=n_eval, track_stats=True)
     torch.manual_seed(3)   # same initial parameters on every rank
-    agent = EvoAgent(env.get_env_args(), hidden_dims=tuple(args.hidden), learning_rate=args.lr, noise_std_dev=args.sigma,
+    agent = EvoAgent(env.get_env_args(), hidden_dims=tuple(hidden), learning_rate=lr, noise_std_dev=sigma,
                      write_to_csv=False, device_id=local_rank, seed=11, env_id_base=rank * n, total_envs=total,
                      pair_id_base=rank * pairs, total_pairs=world * pairs, max_finished=2 * n)
-    lazy = args.mode == "lazy"
+    lazy = mode == "lazy"
 
     def ev():
         return torch.cuda.Event(enable_timing=True)
 
     out = {"generations": []}
-    for gen in range(args.generations):
+    for gen in range(generations):
         states = env.reset_all(lazy=True) if lazy else env.reset_all()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0, t1, t2 = ev(), ev(), ev()
         t0.record()
-        for _ in range(args.steps):
+        for _ in range(steps):
             actions = agent.step(states)
             states, rewards, dones, _ = env.step_lazy(actions) if lazy else env.step(actions)
             agent.store_async(rewards, dones)
@@ -108,19 +100,46 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             dist.all_reduce(fin, op=dist.ReduceOp.SUM)
         out["generations"].append({
-            "rollout_ms": ms[0].item(), "ms_per_step": ms[0].item() / args.steps, "train_ms": ms[1].item(),
-            "env_steps_per_sec_with_policy": total * args.steps / (ms[0].item() * 1e-3),
+            "rollout_ms": ms[0].item(), "ms_per_step": ms[0].item() / steps, "train_ms": ms[1].item(),
+            "env_steps_per_sec_with_policy": total * steps / (ms[0].item() * 1e-3),
             "episodes_ranked": fin.item(), "mean_return": stats["mean_return"],
             "theta_step_norm": float((theta - theta_before).norm()), "theta_norm": float(theta.norm()),
             "parameters_identical_on_all_ranks": bool(torch.equal(hmin, hmax)),
         })
+    net = agent.network
+    out.update(n_gpus=world, total_envs=total, envs_per_gpu=n, eval_envs_per_gpu=n_eval, steps=steps, window=W,
+               mode=mode, network_shape=list(net.shape), policy_params=sum(w.numel() + b.numel() for w, b in
+                                                                           zip(net.weight_layers, net.bias_layers)),
+               perturbation_bytes_per_gpu=net._eps.numel() * 2, workload=workload,
+               perturbation_storage="fp16 (the reference draws f32; parity shown for fp16-representable eps)",
+               kernels_per_step=["fe_es_forward", "fe_lazy_kernel", "fe_es_store"],
+               fitness_gather="finished-episode lists (global env id, return), all_gather over NCCL")
+    del env, agent, series
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--envs-per-gpu", type=int, default=524288)
+    ap.add_argument("--eval-envs-per-gpu", type=int, default=0)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--generations", type=int, default=3)
+    ap.add_argument("--window", type=int, default=60)
+    ap.add_argument("--hidden", type=int, nargs="*", default=[8])
+    ap.add_argument("--workload", default="c4", choices=["c2", "c4"])
+    ap.add_argument("--mode", default="lazy", choices=["lazy", "dense"])
+    ap.add_argument("--sigma", type=float, default=0.05)
+    ap.add_argument("--lr", type=float, default=0.01)
+    args = ap.parse_args()
+
+    from finenvs_b200 import parallel as par
+
+    rank, world, local_rank = par.init_distributed("nccl")
+    torch.cuda.set_device(local_rank)
+    out = run(rank, world, local_rank, args.envs_per_gpu, args.eval_envs_per_gpu, args.steps, args.generations, args.window,
+              tuple(args.hidden), args.workload, args.mode, args.sigma, args.lr)
     if rank == 0:
-        net = agent.network
-        out.update(n_gpus=world, total_envs=total, envs_per_gpu=n, eval_envs_per_gpu=n_eval, steps=args.steps, window=W,
-                   mode=args.mode, network_shape=list(net.shape), policy_params=sum(w.numel() + b.numel() for w, b in
-                                                                                  zip(net.weight_layers, net.bias_layers)),
-                   perturbation_bytes_per_gpu=net._eps.numel() * 2, workload=args.workload,
-                   fitness_gather="finished-episode lists (global env id, return), all_gather over NCCL")
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
