@@ -676,6 +676,9 @@ fe_pipe_kernel(const FeParams p, const FeSeries s, const FeState st, const Const
 #ifndef FE_GATHER_STAGES
 #define FE_GATHER_STAGES 3 /* slots per mover when they fit (else 2) */
 #endif
+#ifndef FE_GATHER_FLUSH_SPINS
+#define FE_GATHER_FLUSH_SPINS 2000 /* x 100 ns: how long a block waits for the grid's bookkeeping before it leaves the packed dones to the last block out */
+#endif
 constexpr int kGaBook = FE_GATHER_BOOK;
 constexpr int kGaMove = FE_GATHER_MOVE;
 constexpr int kGaThreads = (kGaBook + kGaMove) * 32;
@@ -868,14 +871,24 @@ fe_gather_kernel(const __grid_constant__ CUtensorMap tmap, const FeParams p, con
                 atomicAdd(&sched[2], 1u);
             }
             if (warp == 0) {
+                // The wait normally lasts a few microseconds (the tile counter runs out for every block at the same moment).
+                // Should part of the grid not be resident (fewer SMs available than the device reports), the blocks that
+                // are would wait for blocks that cannot start: after ~0.2 ms the block gives up, flags it in sched[3], and
+                // the last block out — by then every word is staged — sends everything.
+                int ok = 1;
                 if (lane == 0) {
                     const unsigned want = gridDim.x * (unsigned)kGaBook;
-                    while (ld_acquire_gpu(&sched[2]) < want) __nanosleep(100);
+                    int spins = 0;
+                    while (ld_acquire_gpu(&sched[2]) < want) {
+                        if (++spins > FE_GATHER_FLUSH_SPINS) { ok = 0; break; }
+                        __nanosleep(100);
+                    }
+                    if (!ok) atomicOr(&sched[3], 1u);
                 }
-                __syncwarp();
+                ok = __shfl_sync(0xFFFFFFFFu, ok, 0);
                 const int per = (((ntiles_all + (int)gridDim.x - 1) / (int)gridDim.x) + 31) & ~31; // whole lines per block
                 const int w_begin = (int)blockIdx.x * per;
-                const int w_end = w_begin + per < ntiles_all ? w_begin + per : ntiles_all;
+                const int w_end = !ok ? w_begin : w_begin + per < ntiles_all ? w_begin + per : ntiles_all;
                 constexpr int kBatch = 8; // loads in batches ahead of the stores: one L2 round trip per batch, not per word
                 for (int w0 = w_begin + lane; w0 < w_end; w0 += kBatch * 32) {
                     uint32_t v[kBatch];
@@ -1013,12 +1026,22 @@ fe_gather_kernel(const __grid_constant__ CUtensorMap tmap, const FeParams p, con
     __syncthreads();
     if (tid == 0) {
         __threadfence();
+        unsigned send_all = 0;
         if (atomicAdd(&sched[1], 1u) == gridDim.x - 1) {
+            __threadfence();
+            send_all = ld_acquire_gpu(&sched[3]);
             sched[0] = 0;
             sched[1] = 0;
             sched[2] = 0;
+            sched[3] = 0;
             __threadfence();
         }
+        claim[2] = send_all;
+    }
+    if (!kObserve && k.dones_bits_host) { // only after a block gave up its wait above
+        __syncthreads();
+        if (claim[2])
+            for (int w = tid; w < ntiles_all; w += kGaThreads) k.dones_bits_host[w] = __ldcg(k.dones_bits_out + w);
     }
 }
 
