@@ -510,8 +510,19 @@ fe_pipe_kernel(const FeParams p, const FeSeries s, const FeState st, const Const
 
     if (warp < kPipeBook) {
         // ------------------------------------------------------------------ bookkeepers
+        // Zero-copy launches (fe_step_host: the actions sit in mapped host memory, k.rewards_mirror is set): the action and
+        // state loads of this warp's NEXT tile are issued before the current tile's arithmetic, which takes the ~2 us PCIe
+        // read out of every tile's dependency chain (as in the gather kernel, where it is measured).
+        const bool ahead = !kObserve && k.rewards_mirror != nullptr;
+        auto tile_env = [&](int t) { return ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TE + lane; };
+        auto tile_active = [&](int t) { return t < ntiles && lane < TE && tile_env(t) < p.num_envs; };
+        EnvLoads ld, ld_next;
+        ld.seg = 0; ld.ptr = 0; ld.cash = 0.0f; ld.lng = 0.0f; ld.sht = 0.0f; ld.act = 0.0f; ld.margin = 0.0;
+        ld_next = ld;
+        if (ahead && tile_active(warp)) ld = env_load_state(st, actions, tile_env(warp));
         for (int t = warp; t < ntiles; t += kPipeBook) {
             const int q = t % kPipeQ;
+            if (ahead && tile_active(t + kPipeBook)) ld_next = env_load_state(st, actions, tile_env(t + kPipeBook));
             mbar_wait(desc_free(q), ((t / kPipeQ) & 1) ^ 1); // first lap passes immediately
             const int64_t env0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TE;
             const int nvalid = (int)min((int64_t)TE, p.num_envs - env0);
@@ -521,10 +532,14 @@ fe_pipe_kernel(const FeParams p, const FeSeries s, const FeState st, const Const
             if (active) {
                 const int64_t i = env0 + lane;
                 if (kObserve) r = env_observe(p, s, st, k, i);
-                else r = env_step<OutT>(p, s, st, k, i, actions, rewards, dones, stats != nullptr, step);
+                else {
+                    if (!ahead) ld = env_load_state(st, actions, i);
+                    r = env_compute<OutT>(p, s, st, k, i, ld, env_load_bar(p, s, ld), rewards, dones, stats != nullptr, step);
+                }
                 d_row0[q * TE + lane] = r.row0;
                 reinterpret_cast<OutT *>(d_pf + q * TE)[lane] = (OutT)r.posfeat;
             }
+            ld = ld_next;
             if (!kObserve && k.dones_bits_out) { // only set when TE == 32: the tile is one word of the bit-packed dones
                 const unsigned word = __ballot_sync(0xFFFFFFFFu, active && r.done);
                 if (lane == 0) k.dones_bits_out[env0 >> 5] = word;
