@@ -59,6 +59,14 @@ roll = env.capture_rollout(lambda obs: torch.tanh(obs[:, -1, 3:4] * 30.0), 5)
 roll.replay(); roll.replay()
 a = torch.rand((301, 1)) * 2 - 1
 env.step_host(a.pin_memory()); env.step_host(a)
+# host step of the persistent kernels with pinned buffers (zero-copy reads, claim-ahead bookkeepers), both wire formats of the
+# dones: gather packs and sends them itself, pipe through the staging buffer + fe_flush_bits_kernel
+for variant in ("gather", "pipe"):
+    env = TimeSeriesEnv("host", num_intervals=W, series=series, num_envs=1301, seed=3, random_reset="all", random_offset=True,
+                        variant=variant, track_stats=True)
+    a = (torch.rand((1301, 1)) * 2 - 1).pin_memory()
+    for t in range(6):
+        env.step_host(a, packed_dones=bool(t % 2))
 
 # ES: fast (60-8-1), streaming (60-16-4-2), generic (400-6-1 needs W = 80) forward kernels, lazy and dense, eval envs
 for shape, Wn in (((60, 8, 1), 12), ((60, 16, 4, 2), 12), ((400, 6, 1), 80)):
