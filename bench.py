@@ -25,7 +25,8 @@ roofline = DRAM bytes per launch / average launch duration (live, CUDA events), 
            (2264 B per env-step at A=1, W=60, f32 obs, MINUS the 960 B of window reads while the table is
            L2-resident: those never reach DRAM, and counting them gave round 1 a "fraction" of 1.34) and `algorithmic_*`
            (all 2264 B).
-also     = the other BASELINE workloads measured in the same process (N=1: c4, c3 and c5; N>1: c4 and c5), same protocol;
+also     = the other BASELINE workloads measured in the same process (N=1: c4, c3, c5 and c1; N>1: c4 and c5), same protocol;
+           c1 = the reference's native size (1024 envs), the configuration cpu_baseline times the reference on;
            c5 = the ES population rollout (policy forward + env step + return bookkeeping per step, EvoAgent.train() per
            generation; perturbations are stored as fp16 where the reference draws f32).
 collectives (N>1) = device time of the NCCL collectives the path uses outside the step (episode statistics
@@ -73,11 +74,12 @@ def window_read_bytes(W: int, A: int = 1, obs_bytes: int = 4) -> int:
     return W * 4 * A * obs_bytes
 
 
-WORKLOAD_ASSETS = {"c2": 1, "c4": 1, "c3": 30}
-WORKLOAD_DEFAULTS = {"c2": (1 << 20, 60), "c4": (1 << 20, 60), "c3": (65536, 128)}   # (envs per GPU, window)
-WORKLOAD_SERIES = {"c2": (1024 * 252, 252, 0.01), "c3": (1024 * 252, 252, 0.01), "c4": (10_000_000, 390, 0.0005)}
+WORKLOAD_ASSETS = {"c1": 1, "c2": 1, "c4": 1, "c3": 30}
+WORKLOAD_DEFAULTS = {"c1": (1024, 60), "c2": (1 << 20, 60), "c4": (1 << 20, 60), "c3": (65536, 128)}   # (envs per GPU, window)
+WORKLOAD_SERIES = {"c1": (1024 * 252, 252, 0.01), "c2": (1024 * 252, 252, 0.01), "c3": (1024 * 252, 252, 0.01), "c4": (10_000_000, 390, 0.0005)}
 
 WORKLOAD_NAMES = {
+    "c1": "single-asset synthetic GBM daily-bar TimeSeriesEnv, 1024 envs, 60-step window, random actions (the reference's native size)",
     "c3": "30-asset portfolio-allocation env, 65536 envs, 128-step window, transaction costs, 1 B200",
     "c2": "single-asset env, 1M envs, 60-step window, fused step kernel on 1 B200 vs reference",
     "c4": "synthetic minute-bar series of 10M timesteps, 1M envs per GPU with random start offsets, env-sharded",
@@ -658,6 +660,18 @@ def main():
                        "gpu_launches": r["gpu_launches"]}
         if not args.no_c5:
             also["c5"] = measure_es_rollout(rank, world, local_rank)
+        if world == 1 and args.workload != "c1":
+            # BASELINE config 1, the size the reference itself runs at (cpu_baseline times the reference on exactly this):
+            # launch-bound, so what counts is the public step() and the host-buffer call, not a roofline
+            n, win = WORKLOAD_DEFAULTS["c1"]
+            r = measure_workload(torch, par, loader, timer, "c1", n, win, rank, world, local_rank, max(args.steps, 100), args.warmup,
+                                 3, "auto", full=True)
+            also["c1"] = {"workload": WORKLOAD_NAMES["c1"], "envs_per_gpu": n, "window": win, "assets": 1, "value": r["value"],
+                          "unit": UNIT, "ms_per_step": r["ms_per_step"], "kernel": r["roofline"]["kernel"],
+                          "public_step": {k: r["public_step"][k] for k in ("value", "ms_per_step", "api")},
+                          "e2e": {k: r["e2e"][k] for k in ("value", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step", "api")},
+                          "note": "launch-bound: one kernel launch per step; CUDA-graph replay of policy + step: tools/graph_rollout.py",
+                          "gpu_launches": r["gpu_launches"]}
         _SERIES_CACHE.clear()
         if world > 1:
             collectives = measure_collectives(torch, dist, par, dev, world, args.envs)

@@ -2197,8 +2197,12 @@ static int step_host_impl(const FeParams *p, const FeSeries *s, const FeState *s
         // sit on its shared memory while it waits for its actions and write 16-byte PCIe packets (measured W = 60,
         // 1 Mi envs: 1.04 ms zero-copy, 0.77 ms with a copy-engine upload + zero-copy writes, vs 0.36 ms
         // device-resident): those take the chunked copy pipeline below.
+        // Small populations are the exception: there the whole step is a few microseconds and the three copies, two events
+        // and their stream hops of the chunked path cost more than the PCIe round trips (1024 envs: C call 25.6 -> 20.0 us, bit-packed
+        // 35.0 -> 24.8 us; profiles/r02_e2e_probe_small_populations.txt), so tile / direct launches of <= 32 Ki envs go zero-copy too.
         const StepKernel kk = choose_kernel(*p, s->obs_table && st->sched, p->out_f64 != 0, sms).kern;
-        if (ok && kk != K_TILE && kk != K_DIRECT) {
+        const bool small = n <= 32768;
+        if (ok && ((kk != K_TILE && kk != K_DIRECT) || small)) {
             const float *a = (const float *)aa.devicePointer;
             int32_t *dmirror = dones_host ? (int32_t *)ad.devicePointer : nullptr;
             uint32_t *bmirror = dones_bits_host ? (uint32_t *)ad.devicePointer : nullptr;
@@ -2212,9 +2216,13 @@ static int step_host_impl(const FeParams *p, const FeSeries *s, const FeState *s
             if (rc) return rc;
             if (dones_bits_host && packed_inline != 1) {
                 const int64_t nwords = (n + 31) / 32;
-                if (packed_inline == 0)
-                    fe_pack_dones_kernel<<<(unsigned)((n + 255) / 256), 256, 0, q>>>(dones_dev, n, stage);
-                fe_flush_bits_kernel<<<(unsigned)((nwords + 255) / 256), 256, 0, q>>>(stage, nwords, (uint32_t *)ad.devicePointer);
+                if (packed_inline == 0 && small) { // a handful of words: straight to the host, one launch less
+                    fe_pack_dones_kernel<<<(unsigned)((n + 255) / 256), 256, 0, q>>>(dones_dev, n, (uint32_t *)ad.devicePointer);
+                } else {
+                    if (packed_inline == 0)
+                        fe_pack_dones_kernel<<<(unsigned)((n + 255) / 256), 256, 0, q>>>(dones_dev, n, stage);
+                    fe_flush_bits_kernel<<<(unsigned)((nwords + 255) / 256), 256, 0, q>>>(stage, nwords, (uint32_t *)ad.devicePointer);
+                }
                 if ((rc = (int)cudaGetLastError())) return rc;
             }
             return (int)cudaStreamSynchronize(q);
