@@ -174,7 +174,8 @@ int fe_materialize(const FeParams *p, const FeSeries *s, const int64_t *obs_row0
 /* Same step driven from HOST buffers (the call a non-torch embedder makes).  When actions_host, rewards_host and
  * dones_host are all pinned (cudaHostAlloc / cudaHostRegister), the step kernel itself reads the actions from and
  * writes rewards / dones to host memory over PCIe (zero-copy: no separate upload or download); otherwise the envs
- * are cut into chunks whose upload, kernel and download are pipelined over three streams.  Either way the call
+ * are cut into chunks whose upload, kernel and download are pipelined over three streams (also with pinned buffers for
+ * the tile / direct variants above 32 Ki envs, whose blocks would wait on PCIe holding their shared memory).  Either way the call
  * returns after the results are in rewards_host / dones_host; rewards_dev / dones_dev hold the same values; the
  * observation stays in HBM (obs_dev) for the policy.  actions_dev is scratch (N*A floats). */
 int fe_step_host(const FeParams *p, const FeSeries *s, const FeState *st, const float *actions_host,
@@ -182,7 +183,9 @@ int fe_step_host(const FeParams *p, const FeSeries *s, const FeState *st, const 
                  int32_t *dones_host, FeStats *stats_dev, uint64_t step_counter, void *stream);
 /* fe_step_host with the dones bit-packed on the wire: dones_bits_host holds ceil(N/32) little-endian 32-bit words,
  * bit (i % 32) of word i / 32 = done flag of env i (4 bytes per env -> 1 bit: 12 -> 8.1 bytes per env-step over PCIe,
- * which is what bounds 8 ranks sharing one host).  dones_dev still receives the int32 flags. */
+ * which is what bounds 8 ranks sharing one host).  dones_dev still receives the int32 flags.  The words are built by the
+ * step kernel (one ballot per 32-env tile), staged in actions_dev and leave for the host in full 128-byte lines; with the
+ * gather variant that uses the arrival counters of FeState.sched. */
 int fe_step_host_packed(const FeParams *p, const FeSeries *s, const FeState *st, const float *actions_host,
                         float *actions_dev, void *obs_dev, void *rewards_dev, int32_t *dones_dev, void *rewards_host,
                         uint32_t *dones_bits_host, FeStats *stats_dev, uint64_t step_counter, void *stream);
