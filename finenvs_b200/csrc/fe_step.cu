@@ -713,12 +713,23 @@ __host__ __device__ inline int64_t ga_rows_per_phase(int64_t num_rows, int W, bo
 __host__ __device__ inline size_t ga_table_bytes(int64_t num_rows, int W, bool f64) {
     return (size_t)(1 << ga_phase_shift(f64)) * (size_t)ga_rows_per_phase(num_rows, W, f64) * kGaPitch + 4096;
 }
-// a window must be a legal TMA box row: a multiple of 16 bytes, at most 256 8-byte elements
-__host__ __device__ inline bool ga_window_ok(int W, bool f64) {
-    const int inner = ga_row_bytes(f64) * W;
-    return (inner % 16) == 0 && inner <= 2048;
+// A TMA box row is at most 256 8-byte elements and a multiple of 16 bytes.  Windows of up to 2048 bytes are one box row
+// (one gather4 = the windows of 4 envs).  Longer windows — 60 rows of f64, the reference's own dtype, are 2400 bytes — are
+// fetched in TWO parts: the second half of a window is the tensor row (half window bytes / 80) pitches further on, so one
+// gather4 with the indices (a, a + d, b, b + d) lands the complete windows of 2 envs contiguously; units are then 2 envs.
+// That needs half a window to be a whole number of pitches.  0 = this window has no gather variant.
+__host__ __device__ inline int ga_parts(int W, bool f64) {
+    const int wb = ga_row_bytes(f64) * W;
+    if (W <= 0 || (wb % 16) != 0) return 0;
+    if (wb <= 2048) return 1;
+    if (wb <= 4096 && ((wb / 2) % kGaPitch) == 0 && W <= 128) return 2; // W <= 128: four rounds of position-feature stores
+    return 0;
 }
-__host__ __device__ inline uint32_t ga_slot_pitch(int W, bool f64) { return (4u * ga_row_bytes(f64) * W + 127u) & ~127u; }
+__host__ __device__ inline bool ga_window_ok(int W, bool f64) { return ga_parts(W, f64) != 0; }
+__host__ __device__ inline uint32_t ga_slot_pitch(int W, bool f64) { // one unit: 4 envs (one part) or 2 envs (two parts)
+    const int parts = ga_parts(W, f64);
+    return ((4u / (uint32_t)(parts ? parts : 1)) * ga_row_bytes(f64) * W + 127u) & ~127u;
+}
 template <typename OutT> __host__ __device__ inline size_t gather_desc_bytes() { // tile id + 32 x {row index, feature} per slot
     return ((size_t)kGaQ * (4 + 32 * (4 + sizeof(OutT))) + 127) & ~(size_t)127;
 }
@@ -751,13 +762,17 @@ __device__ __forceinline__ unsigned long long ga_globaltimer() {
 #define GA_ACC(slot, a, b)
 #endif
 
-template <typename OutT, bool kObserve>
+template <typename OutT, bool kObserve, int kParts>
 __global__ void __launch_bounds__(kGaThreads, 1)
 fe_gather_kernel(const __grid_constant__ CUtensorMap tmap, const FeParams p, const FeSeries s, const FeState st, const Consts k,
                  const float *__restrict__ actions, OutT *__restrict__ obs, OutT *__restrict__ rewards,
                  int32_t *__restrict__ dones, FeStats *stats, const uint64_t step_arg, const uint64_t *__restrict__ step_dev,
                  const int S, const int rows_per_phase, unsigned int *__restrict__ sched) {
     constexpr bool kF64 = sizeof(OutT) == 8;
+    constexpr int kUnitEnvs = 4 / kParts;        // envs per unit (one gather4, one bulk store)
+    constexpr int kTileUnits = 32 / kUnitEnvs;   // units per 32-env tile: 8 or 16
+    constexpr int kUnitShift = kParts == 1 ? 3 : 4;
+    static_assert(kParts == 1 || kParts == 2, "a window is fetched in one or two parts");
     extern __shared__ __align__(128) unsigned char smem[];
     const uint64_t step = step_dev ? *step_dev : step_arg;
     const int W = p.window;
@@ -784,7 +799,7 @@ fe_gather_kernel(const __grid_constant__ CUtensorMap tmap, const FeParams p, con
     }
 #endif
     if (tid == 0) {
-        for (int q = 0; q < kGaQ; ++q) { mbar_init(desc_full(q), 1); mbar_init(desc_free(q), 8); }
+        for (int q = 0; q < kGaQ; ++q) { mbar_init(desc_full(q), 1); mbar_init(desc_free(q), kTileUnits); }
         for (int m = 0; m < kGaMove; ++m)
             for (int si = 0; si < kGaMaxStages; ++si) mbar_init(slot_full(m, si), 1);
         claim[0] = 0; claim[1] = 0;
@@ -925,28 +940,35 @@ fe_gather_kernel(const __grid_constant__ CUtensorMap tmap, const FeParams p, con
         const long long mover_t0 = clock64();
 #endif
         const int m = warp - kGaBook;
-        const uint32_t row_b = (uint32_t)ga_row_bytes(kF64) * W, unit_b = 4 * row_b;
+        const uint32_t row_b = (uint32_t)ga_row_bytes(kF64) * W, unit_b = kUnitEnvs * row_b; // row_b: one window
+        const int part_rows = (int)(row_b / 2) / kGaPitch; // two parts: tensor rows from a window's first half to its second
         unsigned char *slots = ring + (size_t)m * S * pitch;
         // position-feature column: env e of a unit owns rows [eW, (e+1)W) of the slot; this lane writes rows eW + lane + 32k
-        constexpr int kRounds = kF64 ? 2 : 4; // ceil(W / 32) for the largest W ga_window_ok() admits (51 / 102)
+        constexpr int kRounds = (kParts == 1 && kF64) ? 2 : 4; // ceil(W / 32) for the largest W ga_parts() admits (51 / 102 / 128)
         uint32_t round_mask = 0;              // bit k: lane + 32k < W
 #pragma unroll
         for (int kk = 0; kk < kRounds; ++kk) round_mask |= (uint32_t)(lane + 32 * kk < W) << kk;
         const uint32_t env_stride = (uint32_t)W * 5; // values per env
         const uint64_t keep = l2_policy_evict_last(), stream_out = l2_policy_evict_first();
-        // unit i of this mover = group (m + i * kGaMove) % 8 of the block's sequence slot (m + i * kGaMove) / 8
+        // unit i of this mover = group (m + i * kGaMove) % kTileUnits of the block's sequence slot (m + i * kGaMove) / kTileUnits
         static_assert((kGaQ & (kGaQ - 1)) == 0, "kGaQ must be a power of two");
         int iss_u = m, iss_si = 0; // lane 0: next unit to issue (unit number within the block, slot)
         int issued = 0;            // lane 0: units whose gather has been issued
         bool open = true;          // lane 0: more units may follow (no "no more tiles" slot seen yet)
         auto issue = [&]() {       // lane 0: gather of the next unit into slot iss_si
-            const int n = iss_u >> 3, g = iss_u & 7, q = n & (kGaQ - 1);
+            const int n = iss_u >> kUnitShift, g = iss_u & (kTileUnits - 1), q = n & (kGaQ - 1);
             GA_CLK(c0);
             mbar_wait(desc_full(q), (n / kGaQ) & 1);
             GA_CLK(c1);
             GA_ACC(4, c0, c1);
             if (d_tile[q] < 0) { open = false; return; }
-            const int4 rows4 = *reinterpret_cast<const int4 *>(d_row + q * 32 + 4 * g);
+            int4 rows4;
+            if constexpr (kParts == 1) {
+                rows4 = *reinterpret_cast<const int4 *>(d_row + q * 32 + 4 * g);
+            } else { // (first half, second half) of env 2g, then of env 2g + 1
+                const int2 r2 = *reinterpret_cast<const int2 *>(d_row + q * 32 + 2 * g);
+                rows4 = make_int4(r2.x, r2.x + part_rows, r2.y, r2.y + part_rows);
+            }
 #ifdef FE_GATHER_NOLOAD
             if (rows4.x == -12345)
 #endif
@@ -974,20 +996,20 @@ fe_gather_kernel(const __grid_constant__ CUtensorMap tmap, const FeParams p, con
         uint32_t slot_phase = 0; // bit si: parity the mover waits for on slot_full(m, si)
         int n_iss = __shfl_sync(0xFFFFFFFFu, issued, 0);
         for (int i = 0; i < n_iss; ++i) {
-            const int n = u >> 3, g = u & 7, q = n & (kGaQ - 1);
+            const int n = u >> kUnitShift, g = u & (kTileUnits - 1), q = n & (kGaQ - 1);
             GA_CLK(c0);
-            if (lane == 0) mbar_wait(slot_full(m, si), (slot_phase >> si) & 1u); // the four windows have landed
+            if (lane == 0) mbar_wait(slot_full(m, si), (slot_phase >> si) & 1u); // the unit's windows have landed
             __syncwarp();
             GA_CLK(c1);
             GA_ACC(0, c0, c1);
             unsigned char *slot = slots + (size_t)si * pitch;
-            const OutT *pf = d_pf + q * 32 + 4 * g;
+            const OutT *pf = d_pf + q * 32 + kUnitEnvs * g;
             OutT *col = reinterpret_cast<OutT *>(slot) + 5 * lane + 4; // position-feature slot of row `lane` of env 0
 #ifdef FE_GATHER_NOPF
             if (pf[0] == (OutT)12345.678)
 #endif
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
+            for (int e = 0; e < kUnitEnvs; ++e) {
                 const OutT v = pf[e];
 #pragma unroll
                 for (int kk = 0; kk < kRounds; ++kk)
@@ -1002,9 +1024,9 @@ fe_gather_kernel(const __grid_constant__ CUtensorMap tmap, const FeParams p, con
             GA_CLK(c2);
             GA_ACC(11, c1b, c2);
             if (lane == 0) {
-                const int64_t env0 = (int64_t)d_tile[q] * 32 + 4 * g;
+                const int64_t env0 = (int64_t)d_tile[q] * 32 + kUnitEnvs * g;
                 const int64_t left = p.num_envs - env0;
-                const int nv = left >= 4 ? 4 : (left > 0 ? (int)left : 0); // < 4 only in the ragged last tile
+                const int nv = left >= kUnitEnvs ? kUnitEnvs : (left > 0 ? (int)left : 0); // fewer only in the ragged last tile
 #ifdef FE_GATHER_NOSTORE
                 if (nv > 4)
 #else
@@ -1878,15 +1900,25 @@ int launch(const FeParams &p, const FeSeries &s, const FeState &st, const float 
         const int64_t rpp = ga_rows_per_phase(p.num_rows, p.window, f64);
         const int64_t total_rows = rpp << ga_phase_shift(f64);
         if (total_rows >= ((int64_t)1 << 31)) return FE_EINVAL;
+        const int parts = ga_parts(p.window, f64);
         CUtensorMap tmap;
-        if ((rc = gather_tensor_map(s.obs_table, total_rows, ga_row_bytes(f64) * p.window, p.device, &tmap))) return rc;
-        auto kern = fe_gather_kernel<OutT, kObserve>;
-        static std::atomic<uint32_t> configured{0};
-        if ((rc = opt_in_smem(kern, configured, p.device))) return rc;
+        if ((rc = gather_tensor_map(s.obs_table, total_rows, ga_row_bytes(f64) * p.window / parts, p.device, &tmap))) return rc;
         const int64_t ntiles = (p.num_envs + 31) / 32;
         const unsigned blocks = (unsigned)(ntiles < sms ? ntiles : sms);
-        kern<<<blocks, kGaThreads, gather_smem_bytes<OutT>(p.window, c.S), stream>>>(
-            tmap, p, s, st, k, actions, (OutT *)obs, (OutT *)rewards, dones, stats, step, step_dev, c.S, (int)rpp, st.sched);
+        const size_t smem = gather_smem_bytes<OutT>(p.window, c.S);
+        if (parts == 1) {
+            auto kern = fe_gather_kernel<OutT, kObserve, 1>;
+            static std::atomic<uint32_t> configured{0};
+            if ((rc = opt_in_smem(kern, configured, p.device))) return rc;
+            kern<<<blocks, kGaThreads, smem, stream>>>(tmap, p, s, st, k, actions, (OutT *)obs, (OutT *)rewards, dones, stats, step,
+                                                       step_dev, c.S, (int)rpp, st.sched);
+        } else {
+            auto kern = fe_gather_kernel<OutT, kObserve, 2>;
+            static std::atomic<uint32_t> configured{0};
+            if ((rc = opt_in_smem(kern, configured, p.device))) return rc;
+            kern<<<blocks, kGaThreads, smem, stream>>>(tmap, p, s, st, k, actions, (OutT *)obs, (OutT *)rewards, dones, stats, step,
+                                                       step_dev, c.S, (int)rpp, st.sched);
+        }
         break;
     }
     case K_PIPE: {

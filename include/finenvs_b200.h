@@ -128,7 +128,9 @@ const char *fe_step_kernel_name(const FeParams *p, const FeSeries *s, const FeSt
  * reset, :423-445, on the read side): the (T,4) log-returns as 5-value rows [lr0..lr3, hole for the position feature],
  * in P = 4 (float) / 2 (double) copies shifted by one row each so that every window start is 16-byte aligned for the TMA
  * engine.  fe_obs_table_bytes: buffer size for (num_rows, window, dtype), 0 when this window has no gather variant
- * (5*W*sizeof(value) must be a multiple of 16 and <= 2048 bytes).  fe_obs_table_build fills a 16-byte aligned buffer of
+ * (a window's 5*W*sizeof(value) bytes must be a multiple of 16 and <= 2048, or <= 4096 with W <= 128 and half of them a
+ * multiple of 80: those windows are fetched in two parts — f32 up to 102 rows in one part, e.g. 128 in two; f64 up to 51 in
+ * one, 60 or 100 in two).  fe_obs_table_build fills a 16-byte aligned buffer of
  * that size from logret_dev (T,4) of the same dtype.  Worth it while the table stays L2-resident (<= 64 MB: ~800 k rows). */
 int64_t fe_obs_table_bytes(int64_t num_rows, int32_t window, int32_t out_f64);
 int fe_obs_table_build(const void *logret_dev, int64_t num_rows, int32_t window, int32_t out_f64, void *table_dev, void *stream);

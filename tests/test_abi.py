@@ -119,10 +119,13 @@ def test_kernel_choice_policy(built):
     assert name(rows=10_000_000, table=True) == "fe_pipe_kernel<float,stream>"   # an obs table of 800 MB would not stay in L2
     assert name(rows=1_000_000, table=True) == "fe_pipe_kernel<float,cached>"
     assert name(f64=1) == "fe_pipe_kernel<double,cached>"
-    assert name(f64=1, table=True) == "fe_pipe_kernel<double,cached>"         # 40 * 60 bytes is more than one TMA row
+    assert name(f64=1, table=True) == "fe_gather_kernel<double>"              # 40 * 60 bytes: two TMA rows of 1200 = 15 * 80 bytes
     assert name(f64=1, W=50, table=True) == "fe_gather_kernel<double>"
+    assert name(f64=1, W=54, table=True) == "fe_pipe_kernel<double,cached>"   # 2160 bytes: half a window is not a whole pitch
     assert name(W=61, table=True) == "fe_pipe_kernel<float,cached>"           # 20 * 61 is not a multiple of 16
-    assert name(W=100, table=True) == "fe_gather_kernel<float>" and name(W=104, table=True) == "fe_pipe_kernel<float,cached>"
+    assert name(W=100, table=True) == "fe_gather_kernel<float>" and name(W=108, table=True) == "fe_pipe_kernel<float,cached>"
+    assert name(W=128, N=1 << 19, table=True) == "fe_gather_kernel<float>"    # two parts of 1280 bytes
+    assert name(W=136, N=1 << 19, table=True) == "fe_pipe_kernel<float,cached>"   # two-part windows stop at 128 rows
     assert name(N=1024) == "fe_tile_kernel<float>" == name(N=1024, table=True)   # config 1: too few tiles per SM
     assert name(W=4, N=1 << 22) == "fe_tile_kernel<float>" and name(W=16, table=True) == "fe_tile_kernel<float>"   # few rows per env
     assert name(W=24) == "fe_pipe_kernel<float,cached>" and name(W=512, N=1 << 17) == "fe_pipe_kernel<float,cached>"
@@ -149,9 +152,12 @@ def test_obs_table_geometry(built):
     L = built.lib()
     assert L.fe_obs_table_bytes(258048, 60, 0) == 4 * (258048 // 4 + 15 + 8) * 80 + 4096      # 20.6 MB for config 2
     assert L.fe_obs_table_bytes(258048, 61, 0) == 0 and L.fe_obs_table_bytes(258048, 62, 0) == 0
-    assert L.fe_obs_table_bytes(258048, 100, 0) > 0 and L.fe_obs_table_bytes(258048, 104, 0) == 0
+    assert L.fe_obs_table_bytes(258048, 100, 0) > 0 and L.fe_obs_table_bytes(258048, 108, 0) == 0
+    assert L.fe_obs_table_bytes(258048, 104, 0) > 0 and L.fe_obs_table_bytes(258048, 128, 0) > 0    # fetched in two parts
+    assert L.fe_obs_table_bytes(258048, 136, 0) == 0
     assert L.fe_obs_table_bytes(258048, 50, 1) == 2 * (258048 // 2 + 25 + 8) * 80 + 4096
-    assert L.fe_obs_table_bytes(258048, 51, 1) == 0 and L.fe_obs_table_bytes(258048, 52, 1) == 0
+    assert L.fe_obs_table_bytes(258048, 51, 1) == 0 and L.fe_obs_table_bytes(258048, 54, 1) == 0
+    assert L.fe_obs_table_bytes(258048, 60, 1) == 2 * (258048 // 2 + 30 + 8) * 80 + 4096            # the reference's dtype, W = 60
     assert L.fe_obs_table_bytes(0, 60, 0) == 0 and L.fe_obs_table_bytes(100, 0, 0) == 0
 
 

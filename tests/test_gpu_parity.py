@@ -43,7 +43,7 @@ def test_cuda_replays_reference_trace(name, dtype, variant):
     if variant == "pipe" and _lib_mod().lib().fe_pipe_envs(int(z["window"]), int(dtype == torch.float64), 0) == 0:
         pytest.skip("window too large for the pipe variant's rings")
     if variant == "gather" and _lib_mod().lib().fe_obs_table_bytes(int(z["prices"].shape[0]), int(z["window"]), int(dtype == torch.float64)) == 0:
-        pytest.skip("this window is not a legal TMA row (5*W*itemsize must be a multiple of 16, <= 2048 bytes)")
+        pytest.skip("this window has no gather variant (5*W*itemsize a multiple of 16 and <= 2048 bytes, or two such halves)")
     if variant == "tile" and _lib_mod().lib().fe_tile_envs(int(z["window"]), int(dtype == torch.float64), 0) == 0:
         pytest.skip("window too large for the tile variant")
     series = stage_trace_series(z, dtype)
@@ -473,9 +473,30 @@ def test_config4_stream_kernel_long_lockstep(dtype):
     assert n_done >= 2 * n
 
 
+@pytest.mark.parametrize("dtype,W,N", [(torch.float64, 60, 40003), (torch.float32, 128, 40001), (torch.float64, 100, 40002),
+                                       (torch.float32, 104, 40003)])
+def test_gather_kernel_two_part_windows_lockstep(dtype, W, N):
+    """Windows longer than one TMA box row (2048 B) — 60 rows of f64, the reference's own observation dtype, or 128 rows of
+    f32 — are fetched in two parts, two envs per gather4 (fe_gather_kernel<.., 2>): lock-step with the oracle through more
+    than two episodes per env, ragged last tile (N % 32 in 1 .. 3: units with fewer than two live envs), statistics on."""
+    from oracle import oracle as orc
+    from finenvs_b200.data import loader
+
+    prices, seg_start, seg_len = _c1_series(W, days=60, bars=31, sigma=0.05, seed=W + N)
+    series = loader.stage_series(prices, seg_start, seg_len, W, "cuda:0", dtype, keep_logret64=True)
+    fs = orc.series_from_prices(prices, seg_start, seg_len, W, logret=series.logret64.cpu().numpy())
+    f64 = dtype == torch.float64
+    env = _env(series, num_envs=N, seed=9, random_reset="all", random_offset=True, obs_dtype=dtype, track_stats=True)
+    assert env.kernel_name() == f"fe_gather_kernel<{'double' if f64 else 'float'}>"
+    assert (8 if f64 else 4) * 5 * W > 2048                                # really the two-part path
+    ref = orc.OracleEnv(fs, num_envs=N, seed=9, reset_mode=2, random_offset=True, out_f64=f64)
+    n_done = _lockstep(env, ref, 70, np.random.default_rng(N), obs_every=5)
+    assert n_done >= 2 * N and int(env.stats()["n_done"].item()) == n_done
+
+
 def test_auto_picks_the_kernels_documented_in_design():
-    """`auto`: gather for large populations over an L2-resident series when 5*W*itemsize is a multiple of
-    16, pipe otherwise (odd windows, long series), tile for small populations, portfolio for A > 1."""
+    """`auto`: gather for large populations over an L2-resident series when the window is one or two legal
+    TMA rows, pipe otherwise (odd windows, long series), tile for small populations, portfolio for A > 1."""
     from finenvs_b200.data import loader
 
     def name(W, N, dtype=torch.float32, rows=80 * 37, **kw):
@@ -487,8 +508,10 @@ def test_auto_picks_the_kernels_documented_in_design():
     assert name(60, 40000, variant="pipe") == "fe_pipe_kernel<float,cached>"
     assert name(61, 40000) == "fe_pipe_kernel<float,cached>"            # 20 * 61 is not a multiple of 16
     assert name(50, 40000, torch.float64) == "fe_gather_kernel<double>"
-    assert name(60, 40000, torch.float64) == "fe_pipe_kernel<double,cached>"   # 40 * 60 = 2400 B > one TMA row
-    assert name(128, 40000) == "fe_pipe_kernel<float,cached>"
+    assert name(60, 40000, torch.float64) == "fe_gather_kernel<double>"        # 40 * 60 = 2400 B: two TMA rows of 15 pitches
+    assert name(54, 40000, torch.float64) == "fe_pipe_kernel<double,cached>"   # 2160 B: half a window is not a whole pitch
+    assert name(128, 40000) == "fe_gather_kernel<float>"                       # 2560 B in two parts
+    assert name(136, 40000) == "fe_pipe_kernel<float,cached>"
     assert name(60, 3000) == "fe_tile_kernel<float>"
     assert name(16, 40000) == "fe_tile_kernel<float>"                   # few rows per env: thread-per-env bookkeeping wins
     assert name(60, 40000, rows=1_000_000 // 37 * 37) == "fe_pipe_kernel<float,cached>"   # table would not stay in L2

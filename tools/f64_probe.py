@@ -1,0 +1,23 @@
+import sys, os
+sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+import torch, bench
+from finenvs_b200.data import loader
+from finenvs_b200.environments import TimeSeriesEnv
+for W, N in ((60, 1 << 20), (48, 1310720), (32, 1966080)):
+    prices, seg_start, seg_len, _ = bench.make_series("c2", W)
+    for dt in (torch.float64, torch.float32):
+        series = loader.stage_series(prices, seg_start, seg_len, W, "cuda:0", dt)
+        env = TimeSeriesEnv("p", num_intervals=W, device_id=0, series=series, num_envs=N, seed=3, random_reset="all", random_offset=True, obs_dtype=dt)
+        env.reset()
+        a = [torch.rand((N, 1), device="cuda") * 2 - 1 for _ in range(4)]
+        obs = torch.empty((N, W, 5), dtype=dt, device="cuda"); r = torch.empty(N, dtype=dt, device="cuda"); d = torch.empty(N, dtype=torch.int32, device="cuda")
+        for i in range(5): env.step_into(a[i % 4], obs, r, d)
+        ms = []
+        for b in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); e0.record()
+            for i in range(20): env.step_into(a[i % 4], obs, r, d)
+            e1.record(); torch.cuda.synchronize(); ms.append(e0.elapsed_time(e1) / 20)
+        gb = obs.numel() * obs.element_size() / 1e9
+        print(W, N, dt, env.kernel_name(), "ms", round(sorted(ms)[2], 4), "obs GB", round(gb, 3), "write TB/s", round(gb / sorted(ms)[2], 3))
+        del env, series, obs
