@@ -1,13 +1,19 @@
+"""Device-resident step time across observation dtypes / windows / kernels (auto vs forced pipe): tools/f64_probe.py"""
 import sys, os
 sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
 import torch, bench
 from finenvs_b200.data import loader
 from finenvs_b200.environments import TimeSeriesEnv
-for W, N in ((60, 1 << 20), (48, 1310720), (32, 1966080)):
+cases = [(60, 1 << 20, torch.float64, "auto"), (60, 1 << 20, torch.float64, "pipe"), (60, 1 << 20, torch.float32, "auto"),
+         (48, 1310720, torch.float64, "auto"), (100, 314560, torch.float64, "auto"), (100, 314560, torch.float64, "pipe"),
+         (104, 604160, torch.float32, "auto"), (104, 604160, torch.float32, "pipe"),
+         (128, 491520, torch.float32, "auto"), (128, 491520, torch.float32, "pipe")]
+for W, N, dt, variant in cases:
     prices, seg_start, seg_len, _ = bench.make_series("c2", W)
-    for dt in (torch.float64, torch.float32):
+    if True:
         series = loader.stage_series(prices, seg_start, seg_len, W, "cuda:0", dt)
-        env = TimeSeriesEnv("p", num_intervals=W, device_id=0, series=series, num_envs=N, seed=3, random_reset="all", random_offset=True, obs_dtype=dt)
+        env = TimeSeriesEnv("p", num_intervals=W, device_id=0, series=series, num_envs=N, seed=3, random_reset="all", random_offset=True,
+                            obs_dtype=dt, variant=variant)
         env.reset()
         a = [torch.rand((N, 1), device="cuda") * 2 - 1 for _ in range(4)]
         obs = torch.empty((N, W, 5), dtype=dt, device="cuda"); r = torch.empty(N, dtype=dt, device="cuda"); d = torch.empty(N, dtype=torch.int32, device="cuda")
