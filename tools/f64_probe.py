@@ -1,6 +1,10 @@
 """Device-resident step time across observation dtypes / windows / kernels (auto vs forced pipe): tools/f64_probe.py"""
-import sys, os
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch, bench
 from finenvs_b200.data import loader
 from finenvs_b200.environments import TimeSeriesEnv
