@@ -109,6 +109,19 @@ def main():
             ms = [host_block(packed) for _ in range(args.blocks)]
             print(f"round {rnd} {'packed' if packed else 'int32 '}: median {np.median(ms):.4f}  min {min(ms):.4f}  max {max(ms):.4f} ms/step")
 
+    # the kernel inside the host-buffer call: events recorded on the stream right before and after each (synchronous) call
+    for packed in (False, True):
+        ks = []
+        for i in range(60):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            env.step_host(ring_host[i % 4], packed_dones=packed)
+            e1.record()
+            e1.synchronize()
+            ks.append(e0.elapsed_time(e1))
+        ks = sorted(ks[10:])
+        print(f"GPU time between events around one step_host call ({'packed' if packed else 'int32 '}): median {ks[len(ks) // 2]:.4f}  min {ks[0]:.4f} ms")
+
     # the C call alone (no Python step_host around it): arguments prepared once
     a_dev, r_dev, d_dev, rewards, dones, done_bits = env._host_bufs
     obs2 = torch.empty((N, W, 5), dtype=torch.float32, device="cuda:0")
