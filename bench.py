@@ -32,8 +32,9 @@ also     = the other BASELINE workloads measured in the same process (N=1: c4, c
 collectives (N>1) = device time of the NCCL collectives the path uses outside the step (episode statistics
            all-reduce, ES fitness all-gather, ES gradient all-reduce).
 cpu_baseline / --impl reference = the reference's OWN TimeSeriesEnv.step (unmodified, from baseline/_ref,
-           device_id=-1) on the box's host cores, thread count forced; the C/OpenMP oracle port is reported
-           beside it as `cpu_port`.
+           device_id=-1) on the box's host cores, thread count forced: at its native 1024 envs, widened to 65 536, and at
+           the GPU arm's own 1 Mi envs (`same_config_run`, ~2.6 s per step; skipped on hosts with < 64 GB free); `value` is
+           the BEST of the all-thread runs (conservative); the C/OpenMP oracle port is reported beside it as `cpu_port`.
 """
 from __future__ import annotations
 
@@ -325,9 +326,21 @@ class ReferenceRunner:
         return N * n / dt, dt / n, n
 
 
+def host_mem_available_gb() -> float:
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable:"):
+                    return int(line.split()[1]) / 1e6
+    except Exception:
+        pass
+    return 0.0
+
+
 def reference_baseline(W: int, steps: int, warmup: int, budget_each_s: float, with_single_thread: bool, port_workload: str,
-                       widened_envs: int = 65536):
-    """All CPU numbers of one run: the real reference at C1 (N=1024) and widened N=65 536, and the C port."""
+                       widened_envs: int = 65536, full_envs: int = 0):
+    """All CPU numbers of one run: the real reference at C1 (N=1024), widened to N=65 536 and — full_envs > 0, the host has
+    the memory (the step makes ~25 GB of transient copies at 1 Mi envs) — at the GPU arm's own population; and the C port."""
     import torch
     from baseline import reference as ref
 
@@ -339,14 +352,18 @@ def reference_baseline(W: int, steps: int, warmup: int, budget_each_s: float, wi
         out["reference_constructor_s"] = rr.construct_s
         sizes = [rr.native_envs] + ([widened_envs] if widened_envs > rr.native_envs else [])
         plan = [(n, ncpu) for n in sizes] + ([(n, 1) for n in sizes] if with_single_thread else [])
+        if full_envs > max(sizes) and host_mem_available_gb() >= 64.0:
+            plan.append((full_envs, ncpu))   # the exact configuration of the GPU arm: ~2.6 s per step, all threads only
         for N, th in plan:
             wu = warmup if N <= 4096 else 1
-            v, sps, n = rr.run(N, th, steps if N <= 4096 else max(3, min(steps, 8)), wu, budget_each_s)
+            v, sps, n = rr.run(N, th, steps if N <= 4096 else (max(3, min(steps, 8)) if N <= 65536 else 3), wu, budget_each_s)
             run = {"impl": "reference TimeSeriesEnv.step (torch eager, device_id=-1)", "envs": N, "threads": th, "value": v,
                    "ms_per_step": sps * 1e3, "steps": n}
             out["runs"].append(run)
             if th == ncpu and (best is None or v > best["value"]):
                 best = run
+            if N == full_envs and th == ncpu:
+                out["same_config_run"] = run
         rr.close()
     sample = min(WORKLOAD_DEFAULTS[port_workload][0], 262144 // WORKLOAD_ASSETS[port_workload] // (2 if port_workload == "c3" else 1))
     pv, psps, pth, pn = cpu_port_throughput(WORKLOAD_DEFAULTS[port_workload][1], port_workload, sample, 10_000, 3, min(budget_each_s, 8.0))
@@ -367,7 +384,8 @@ def cpu_baseline_block(rb: dict) -> dict:
                        f"torch.set_num_threads({best['threads']}); best of the all-thread runs"),
             "ms_per_step": best["ms_per_step"], "cpu_count": rb["cpu_count"], "cpu_model": rb["cpu_model"], "torch": rb["torch"],
             "runs": rb["runs"], "cpu_port": rb["cpu_port"],
-            "not_timed": "the 1 Mi-env reference step (4 transient ~10 GB copies per step) is not timed"}
+            **({"same_config_run": rb["same_config_run"]} if "same_config_run" in rb else
+               {"not_timed": "the reference step at the GPU arm's full population (~25 GB of transient copies per step at 1 Mi envs)"})}
 
 
 def run_reference_arm(args, rank: int):
@@ -375,7 +393,8 @@ def run_reference_arm(args, rank: int):
     if rank != 0:
         return
     force_host_threads()
-    rb = reference_baseline(60, args.steps, args.warmup, 45.0, True, args.workload, args.ref_widened_envs)
+    full = args.envs if (args.workload == "c2" and args.ref_widened_envs > 0) else 0
+    rb = reference_baseline(60, args.steps, args.warmup, 45.0, True, args.workload, args.ref_widened_envs, full)
     cb = cpu_baseline_block(rb)
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -712,7 +731,8 @@ def main():
     if prev_affinity is not None:
         os.sched_setaffinity(0, prev_affinity)   # the CPU baseline uses every host core
     if world == 1 and not args.no_cpu_baseline:
-        rb = reference_baseline(60, 30, 3, 10.0, False, args.workload, args.ref_widened_envs)
+        full = args.envs if (args.workload == "c2" and args.ref_widened_envs > 0) else 0
+        rb = reference_baseline(60, 30, 3, 10.0, False, args.workload, args.ref_widened_envs, full)
         line["cpu_baseline"] = cpu_baseline_block(rb)
     print(json.dumps(line), flush=True)
     if world > 1:
