@@ -823,7 +823,7 @@ fe_gather_kernel(const __grid_constant__ CUtensorMap tmap, const FeParams p, con
         // ~2 us.  There a claim is taken one tile AHEAD of the tile being computed and the first-hop loads of the claimed
         // tile (action and per-env state) are issued at once, in flight while the current tile is computed, so that the
         // read no longer sits in every tile's dependency chain (measured c2, 1 Mi envs, zero-copy: kernel 0.253 -> 0.2305 ms,
-        // the device-resident time; profiles/r02_e2e_probe_ahead.txt).  Device-resident launches claim tile by tile: holding
+        // the device-resident time; profiles/r02_e2e_probes.txt, call 3).  Device-resident launches claim tile by tile: holding
         // a second claim cost them 0.5 % (tail balance).
         const bool ahead = !kObserve && k.rewards_mirror != nullptr;
         auto take_claim = [&](int &n, int &t) { // sequence slot of this block, tile of the grid (>= ntiles_all: none left)
