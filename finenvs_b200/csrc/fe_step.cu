@@ -683,7 +683,7 @@ fe_pipe_kernel(const FeParams p, const FeSeries s, const FeState st, const Const
 //                               and issues the gather of unit i + S into it.
 // ------------------------------------------------------------------------------------------
 #ifndef FE_GATHER_BOOK
-#define FE_GATHER_BOOK 6 /* measured c2: 6 -> 0.2525 ms, 8 -> 0.2655 ms (profiles/r02_gather_README.txt) */
+#define FE_GATHER_BOOK 6 /* measured c2: 6 -> 0.2525 ms, 8 -> 0.2655 ms (profiles/r02_gather_allwait.txt) */
 #endif
 #ifndef FE_GATHER_MOVE
 #define FE_GATHER_MOVE 12
@@ -811,7 +811,7 @@ fe_gather_kernel(const __grid_constant__ CUtensorMap tmap, const FeParams p, con
         // ------------------------------------------------------------------ bookkeepers
         // Tiles are CLAIMED, not pre-assigned: SMs differ by ~15 % in how fast they move this traffic (position relative
         // to the L2 slices / the two dies), and with a static round-robin the slowest SM set the kernel time (232 ... 273 us
-        // per block, profiles/r02_gather_clocks.txt).  A claim = (next sequence number of this block, next tile of the
+        // per block, profiles/r02_gather_sweeps.txt, sweep 5).  A claim = (next sequence number of this block, next tile of the
         // grid), taken together under a block-local lock so that sequence order = tile order: once a sequence slot says
         // "no more tiles", every later one does.
         const int shift = ga_phase_shift(kF64);
